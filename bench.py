@@ -1,0 +1,334 @@
+#!/usr/bin/env python3
+"""bench.py — MPC solves/sec of the hot path on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic requests: config C3 of BASELINE.json
+(batch 65536 per GPU, control_steps = 10, footprint + costmap on a 1000x1000 grid, opt_tolerance = 1e-3) —
+the configuration the >= 1e6 solves/s target is quoted on.  Weak scaling: every rank solves its own 65536
+requests of the same distribution and the solved (vx, vy, omega) are all-gathered over NCCL inside the step.
+
+  value      solves/s with the requests already resident in HBM (kernel + gather), CUDA-event time, max over ranks
+  e2e        solves/s through neompc_solve_batch with pinned HOST buffers: H2D requests, solve, D2H responses
+  roofline   algorithmic bytes (76 B/solve + costmap once per launch) / measured kernel time
+  cpu_baseline  the reference algorithm (oracle port of srv.py:363-364, scipy SLSQP) on a bounded sample, all host cores
+
+`--impl reference` times only the CPU reference arm (rank 0), same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "mpc_solves_per_sec"
+UNIT = "solves/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+_W = {}
+
+
+def _cpu_init(cfg, batch, seed_off):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import oracle
+    from oracle.costmap import GridCostmap, FreeSpaceCostmap
+    from neo_mpc_planner2_b200 import workloads
+    wl = workloads.config(cfg, batch=batch)
+    _W["wl"] = wl
+    _W["p"] = oracle.MpcParams(**wl.params)
+    _W["cm"] = (GridCostmap(wl.cells, wl.resolution, wl.origin_x, wl.origin_y) if wl.cells is not None
+                else FreeSpaceCostmap())
+    _W["oracle"] = oracle
+
+
+def _cpu_solve(i):
+    """One reference solve, exactly the reference's call (srv.py:363-364): cold start, SLSQP, ftol = opt_tolerance."""
+    oracle, wl, p, cm = _W["oracle"], _W["wl"], _W["p"], _W["cm"]
+    from oracle.mpc_oracle import footprint_world
+    prob = oracle.Problem.from_record(wl.requests[i])
+    fpw = footprint_world(wl.footprint, prob.pose_x, prob.pose_y, prob.pose_yaw)
+    res = oracle.slsqp_solve(p, cm, fpw, prob)
+    return i, float(res.fun), res.x.astype(np.float64)
+
+
+def cpu_reference_rate(cfg, sample, cores, repeats=1):
+    """solves/s of the reference algorithm on `sample` problems of the workload with `cores` processes."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg, max(sample, 64), 0)) as pool:
+        pool.map(_cpu_solve, range(min(cores, sample)))          # warm the workers (imports, first call)
+        times, last = [], None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            last = pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
+            times.append(time.perf_counter() - t0)
+    return sample / min(times), times, last
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or 64
+    for _ in range(args.warmup):
+        pass                                                     # pool warm-up happens inside cpu_reference_rate
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.config, max(sample, 64), 0)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_solve, range(min(cores, sample)))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
+        dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    wl_name, n_steps = _workload_name(args.config)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "control_steps": n_steps, "opt_tolerance": 1e-3,
+                   "solver": "scipy SLSQP, finite-difference gradients (oracle port of srv.py:363-364)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {sample} problems of the workload per step, cold start, "
+                                   f"multiprocessing.Pool({cores})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def _workload_name(cfg):
+    from neo_mpc_planner2_b200 import workloads
+    wl = workloads.config(cfg, batch=64)
+    names = {"c2": "C2 batch=4096 control_steps=3 costmap 200x200",
+             "c3": "C3 batch=65536/GPU control_steps=10 footprint+costmap 1000x1000",
+             "c4": "C4 batch=131072/GPU control_steps=20 costmap 1000x1000",
+             "c5": "C5 fleet sweep 100k poses x 8 carrots, control_steps=10, costmap 2000x2000"}
+    return names.get(cfg, cfg), wl.control_steps
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from neo_mpc_planner2_b200 import workloads
+    from neo_mpc_planner2_b200.abi import REQUEST_DTYPE, RESPONSE_DTYPE
+    from neo_mpc_planner2_b200.solver import BatchSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the solve)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    per_gpu = {"c2": 4096, "c3": 65536, "c4": 131072, "c5": 100000}[args.config]
+    if args.batch:
+        per_gpu = args.batch
+    # every rank: same map, its own slice of the request distribution (seeded by rank)
+    wl = workloads.config(args.config, batch=per_gpu, seed=None if rank == 0 else 1000 + rank)
+    n = wl.batch
+    n_steps = wl.control_steps
+    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes)
+    solver.load_workload(wl)
+    G, S = solver.tiling
+
+    req_host = torch.from_numpy(wl.requests.view(np.uint8).reshape(n, REQUEST_DTYPE.itemsize)).pin_memory()
+    resp_host = torch.empty((n, RESPONSE_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    d_reqs = req_host.to(dev)
+    d_out = torch.empty((n, RESPONSE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_twist = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d_all = torch.empty((world * n, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(k_ev=None):
+        if k_ev is not None:
+            k_ev[0].record(stream)
+        solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_twist.data_ptr(), None, stream.cuda_stream)
+        if k_ev is not None:
+            k_ev[1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_twist)          # the single collective of the path
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = solver.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                                    # L2 flush between timed iterations (untimed)
+        evs[k][0].record(stream)
+        step((evs[k][2], evs[k][3]))
+        evs[k][1].record(stream)
+    barrier()
+    launches = solver.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b, _, _ in evs]
+    kern_ms = [c.elapsed_time(d) for _, _, c, d in evs]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (H2D + solve + D2H inside the timed region)
+    for _ in range(2):
+        solver.solve_raw(req_host.data_ptr(), n, resp_host.data_ptr())
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.solve_raw(req_host.data_ptr(), n, resp_host.data_ptr())
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+    clocks = sampler.stop()
+
+    resp = np.frombuffer(resp_host.numpy().tobytes(), dtype=RESPONSE_DTYPE)
+    iters_med = float(np.median(resp["iters"]))
+    evals_mean = float(resp["evals"].mean())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        bytes_per_solve = wl.algorithmic_bytes_per_solve(n)
+        k_ms = float(np.mean(kern_ms))
+        achieved = bytes_per_solve * n / (k_ms * 1e-3) / 1e9
+        wl_name, _ = _workload_name(args.config)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "batch_per_gpu": n, "control_steps": n_steps,
+                       "opt_tolerance": float(wl.params["opt_tolerance"]), "lanes_per_instance": G,
+                       "steps_per_lane": S, "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
+                       "parallelism": f"batch sharded over {world} GPU(s), one NCCL all-gather of (vx,vy,omega)"
+                       if world > 1 else "single GPU", "cold_start": True,
+                       "iters_median": iters_med, "evals_mean": evals_mean},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
+                         "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
+                         "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * REQUEST_DTYPE.itemsize),
+                    "d2h_bytes_per_step": int(n * RESPONSE_DTYPE.itemsize), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "neompc_solve_batch (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample or 96
+            rate, times, _ = cpu_reference_rate(args.config, sample, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} problems of the same workload, cold start, scipy SLSQP "
+                                              f"as srv.py:363-364, multiprocessing.Pool({cores}), {times[0]:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per instance (0 = auto)")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+/*
+ * neompc.h — C ABI of libneompc: the batched receding-horizon MPC solve of neo_mpc_planner2 on B200.
+ *
+ * This is the drop-in boundary for the reference's hot path.  Today that path is reached through the
+ * ROS 2 service "optimizer" (neo_srvs2/srv/Optimizer): client created at src/NeoMpcPlanner.cpp:308,
+ * request built at :240-246, blocking call at :248-250, twist read at :252; server side registered at
+ * neo_mpc_planner2/mpc_optimization_server.py:105 and handled by MpcOptimizationServer.optimizer
+ * (:349-403).  libneompc replaces the service hop by an in-process call: plain pointers and sizes, no
+ * exceptions, no ROS / torch types.  Every function returns NEOMPC_OK (0) or a negative error code;
+ * neompc_last_error() gives the message.  There is NO CPU fallback: creation fails without a CUDA device.
+ *
+ * Reference paths below are relative to /root/reference ("srv.py" = neo_mpc_planner2/mpc_optimization_server.py,
+ * "cpp" = src/NeoMpcPlanner.cpp).
+ */
+#ifndef NEOMPC_H_
+#define NEOMPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEOMPC_VERSION 100            /* 0.1.0 */
+#define NEOMPC_MAX_CONTROL_STEPS 64
+#define NEOMPC_MAX_FOOTPRINT_VERTICES 16
+#define NEOMPC_STATELESS 0xFFFFFFFFu  /* neompc_request.instance_id: cold start, no per-instance state */
+
+/* error codes */
+enum {
+  NEOMPC_OK = 0,
+  NEOMPC_ERR_INVALID = -1,     /* bad argument / parameter */
+  NEOMPC_ERR_NO_DEVICE = -2,   /* no usable CUDA device (there is no CPU fallback) */
+  NEOMPC_ERR_CUDA = -3,        /* a CUDA runtime call failed */
+  NEOMPC_ERR_STATE = -4        /* instance id beyond the reserved capacity */
+};
+
+/* costmap cell encodings (semantics declared in DESIGN.md "Costmap semantics"; the reference reads its
+ * costmap through the un-vendored neo_nav2_py_costmap2D package, call sites srv.py:246-247,257,262-263,332-333,343) */
+enum {
+  NEOMPC_ENC_OCCUPANCY = 0,    /* nav_msgs/OccupancyGrid: 0..100 -> v/100, anything else (unknown) -> 0 */
+  NEOMPC_ENC_NAV2_RAW = 1      /* nav2 costmap_raw: 0..254 -> v/254, 255 (no information) -> 0 */
+};
+
+/*
+ * Solver parameters: the reference's ROS parameters (declared srv.py:49-75, read :78-103) as one POD,
+ * plus a few solver knobs that have no reference counterpart (0 = library default).
+ * 128 bytes.
+ */
+typedef struct neompc_params {
+  float acc_x_limit, acc_y_limit, acc_theta_limit;                 /* srv.py:49-51, used :385-391 */
+  float min_vel_x, min_vel_y, min_vel_trans, min_vel_theta;        /* srv.py:53-56 (min_vel_trans unused, as in the reference) */
+  float max_vel_x, max_vel_y, max_vel_trans, max_vel_theta;        /* srv.py:58-61; bounds :127-133, disc constraint :157-158 */
+  float w_trans, w_orient, w_control, w_terminal;                  /* srv.py:63-66 */
+  float w_costmap, w_footprint;                                    /* srv.py:67-68 */
+  float waiting_time;                                              /* srv.py:70 (initial value only; threshold is 3.0 s, :380) */
+  float low_pass_gain;                                             /* srv.py:71, used :366-367 */
+  float opt_tolerance;                                             /* srv.py:72 (SLSQP ftol there; see DESIGN.md for its meaning here) */
+  float prediction_horizon;                                        /* srv.py:73 */
+  int32_t control_steps;                                           /* srv.py:75; 1..NEOMPC_MAX_CONTROL_STEPS */
+  int32_t max_iterations;      /* L-BFGS iteration cap (default 100 = SLSQP's maxiter default) */
+  int32_t lbfgs_memory;        /* history pairs, 1..8 (default 5) */
+  float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254); default 1e-2 */
+  int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
+  int32_t reserved[6];
+} neompc_params;
+
+/*
+ * One MPC problem = one neo_srvs2/srv/Optimizer request (fields: cpp:241-246; consumed srv.py:350-355),
+ * planar form, float32, 64 bytes.  Orientations are yaw angles extracted with the reference's
+ * euler_from_quaternion (srv.py:160-180) by whoever marshals the request (neompc_pack_requests does it
+ * on the device from full quaternions).
+ */
+typedef struct neompc_request {
+  float vel_x, vel_y, vel_theta;          /* current_vel.linear.x / .y, .angular.z           (srv.py:216-218) */
+  float carrot_x, carrot_y, carrot_yaw;   /* carrot_pose, robot base frame                    (srv.py:211,219) */
+  float goal_x, goal_y, goal_yaw;         /* goal_pose, plan frame                            (srv.py:212,266) */
+  float pose_x, pose_y, pose_yaw;         /* current_pose, costmap global frame; true yaw     (srv.py:315-317) */
+  float pose_yaw_objective;               /* yaw the objective's costmap rollout starts from: the reference
+                                             mixes goal_pose.orientation.w into it (srv.py:213).  Set it to
+                                             pose_yaw to switch the quirk off. */
+  float control_interval;                 /* 1 / controller_frequency                         (cpp:246, srv.py:385-391) */
+  float delta_t;                          /* wall-clock time since this instance's previous call (srv.py:369-371) */
+  uint32_t instance_id;                   /* row of the per-instance state (warm start, last_control, collision
+                                             latch ...), or NEOMPC_STATELESS */
+} neompc_request;
+
+/* neompc_response.status: how the solver stopped */
+enum {
+  NEOMPC_STATUS_CONVERGED = 0,   /* projected-gradient tolerance met  -> reference "x.success" path (srv.py:397-398) */
+  NEOMPC_STATUS_MAXITER = 1,     /* iteration cap                     -> reference failure path      (srv.py:399-400) */
+  NEOMPC_STATUS_LINESEARCH = 2   /* no further decrease found (e.g. at a costmap cell edge); treated as converged */
+};
+/* neompc_response.flags */
+enum {
+  NEOMPC_FLAG_COLLISION = 1,            /* self.collision after this call        (srv.py:338-339,380-382) */
+  NEOMPC_FLAG_COLLISION_FOOTPRINT = 2,  /* self.collision_footprint              (srv.py:343-347) */
+  NEOMPC_FLAG_NEW_GOAL = 4,             /* the new-goal reset ran                (srv.py:358-361) */
+  NEOMPC_FLAG_STOPPED = 8               /* zero twist returned                   (srv.py:374-377) */
+};
+
+/* Optimizer response (output_vel.twist.linear.x/.y, .angular.z; cpp:252, srv.py:375-377,389-391) + diagnostics. 32 bytes. */
+typedef struct neompc_response {
+  float vx, vy, omega;
+  float cost;          /* reference objective J (srv.py:204-269) at the solver's solution, float32 */
+  uint32_t iters;      /* L-BFGS iterations */
+  uint32_t evals;      /* objective evaluations */
+  uint32_t status;
+  uint32_t flags;
+} neompc_response;
+
+/* Full-fidelity mirror of neo_srvs2/srv/Optimizer.Request in float64 with quaternions, for callers that hold
+ * ROS messages (the plugin).  neompc_pack_requests converts these to neompc_request on the device. */
+typedef struct neompc_optimizer_request {
+  double current_vel[6];        /* Twist: linear xyz, angular xyz */
+  double carrot_pose[7];        /* position xyz, orientation xyzw */
+  double goal_pose[7];
+  double current_pose[7];
+  double control_interval;
+  double delta_t;
+  uint32_t instance_id;
+  uint32_t switch_opt;          /* carried, unused — as in the reference (srv.py:354) */
+} neompc_optimizer_request;
+
+typedef struct neompc_handle neompc_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+/* Replaces client creation + wait-for-service in NeoMpcPlanner::configure (cpp:308, :325-330) and the server's
+ * constructor (srv.py:44-152).  device: CUDA ordinal (>= 0). */
+int neompc_create(const neompc_params* params, int device, neompc_handle** out);
+int neompc_destroy(neompc_handle* h);
+/* Replaces the dynamic-parameter callback (srv.py:405-439); takes effect from the next solve. */
+int neompc_set_params(neompc_handle* h, const neompc_params* params);
+int neompc_get_params(const neompc_handle* h, neompc_params* out);
+const char* neompc_last_error(const neompc_handle* h);   /* h may be NULL: last error of neompc_create on this thread */
+int neompc_version(void);
+/* sizeof() of the POD records as compiled, for binding self-checks: out[0..3] = request, response, params, optimizer_request */
+int neompc_abi_sizes(size_t out[4]);
+
+/* ---- environment ------------------------------------------------------------------------------------------ */
+/* Costmap2d(self) (srv.py:118).  cells: row-major uint8 [height][width], copied to the device (host pointer).
+ * cells == NULL removes the costmap (free space everywhere: BASELINE config C1). */
+int neompc_set_costmap(neompc_handle* h, const uint8_t* cells, uint32_t width, uint32_t height,
+                       double resolution, double origin_x, double origin_y, int encoding);
+/* Same, cells already on the device (copied device-to-device on the handle's stream). */
+int neompc_set_costmap_device(neompc_handle* h, const uint8_t* d_cells, uint32_t width, uint32_t height,
+                              double resolution, double origin_x, double origin_y, int encoding);
+/* Robot-frame footprint polygon (x0,y0,x1,y1,...).  The reference receives the world-frame polygon from
+ * /local_costmap/published_footprint (srv.py:140-144,154-155); here it is placed at each request's current pose. */
+int neompc_set_footprint(neompc_handle* h, const float* xy, int n_vertices);
+
+/* ---- per-instance state (srv.py:115-117,136,138,146-149: initial_guess, last_control, waiting_time, collision,
+ *      collision_footprint, old_goal) ---------------------------------------------------------------------- */
+int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances);
+int neompc_reset_state(neompc_handle* h, const uint32_t* ids, size_t n);     /* ids == NULL: all */
+/* Test/inspection hook: copies one instance's state to the host.  initial_guess: 3*control_steps floats. */
+int neompc_get_state(neompc_handle* h, uint32_t id, float* initial_guess, float last_control[3],
+                     float* waiting_time, uint32_t* flags);
+
+/* ---- the hot path: MpcOptimizationServer.optimizer (srv.py:349-403) for n requests --------------------------- */
+/* Host buffers (what NeoMpcPlanner::computeVelocityCommands calls with n = 1, replacing cpp:240-252).
+ * Synchronous: H2D copy, solve, D2H copy.  plan_or_null: n * 3*control_steps floats, the solver's solution
+ * (the "x.x" of srv.py:363 before the low-pass), e.g. to publish local_plan (srv.py:271-310). */
+int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n,
+                       neompc_response* out, float* plan_or_null);
+/* Device buffers, asynchronous on `stream` (a cudaStream_t; NULL = the handle's own stream).
+ * twist_or_null: n*3 floats (vx,vy,omega) packed — the payload of the multi-GPU gather. */
+int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, size_t n,
+                              neompc_response* d_out, float* d_twist_or_null, float* d_plan_or_null,
+                              void* stream);
+/* Message-level entry: float64 quaternion requests on the host -> device pack (euler_from_quaternion incl. the
+ * goal-w quirk, srv.py:160-180, :211-213) -> solve -> responses on the host. */
+int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, size_t n,
+                      neompc_response* out, float* plan_or_null);
+/* Device-side packing only (d_msgs, d_reqs device pointers), asynchronous on `stream`. */
+int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n,
+                         neompc_request* d_reqs, void* stream);
+
+/* ---- test hooks ------------------------------------------------------------------------------------------- */
+/* objective(cmd_vel) (srv.py:204-269) and its analytic gradient for n (request, u) pairs; host buffers.
+ * u: n * 3*control_steps.  J: n.  grad_or_null: n * 3*control_steps (gradient of the smoothed objective the
+ * solver uses; costmap/footprint terms are piecewise constant and contribute 0). */
+int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const float* u, size_t n,
+                          float* J, float* grad_or_null);
+/* Number of kernels this handle has launched so far. */
+uint64_t neompc_launch_count(const neompc_handle* h);
+/* Lanes-per-instance / steps-per-lane the dispatcher uses for the current parameters. */
+int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* steps_per_lane);
+
+/* pinned host memory for the host-buffer entry points (optional; any host memory works) */
+int neompc_host_alloc(void** ptr, size_t bytes);
+int neompc_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEOMPC_H_ */

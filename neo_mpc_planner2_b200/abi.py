@@ -32,6 +32,19 @@ RESPONSE_DTYPE = np.dtype([
 ], align=False)
 assert RESPONSE_DTYPE.itemsize == 32
 
+# neompc_optimizer_request — float64 mirror of neo_srvs2/srv/Optimizer.Request with quaternions, 240 bytes
+MSG_DTYPE = np.dtype([
+    ("current_vel", "<f8", (6,)),      # Twist: linear xyz, angular xyz
+    ("carrot_pose", "<f8", (7,)),      # position xyz, orientation xyzw
+    ("goal_pose", "<f8", (7,)),
+    ("current_pose", "<f8", (7,)),
+    ("control_interval", "<f8"),
+    ("delta_t", "<f8"),
+    ("instance_id", "<u4"),
+    ("switch_opt", "<u4"),
+], align=False)
+assert MSG_DTYPE.itemsize == 240
+
 # neompc_response.status
 STATUS_CONVERGED = 0
 STATUS_MAXITER = 1

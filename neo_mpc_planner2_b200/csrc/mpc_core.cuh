@@ -1,0 +1,834 @@
+// mpc_core.cuh — the per-instance MPC solve: rollout, cost, analytic gradient, projection onto box∩disc,
+// projected L-BFGS, and the optimizer() epilogue.  One *lane group* of G lanes (G = 1..32, a power of two,
+// G lanes of one warp) owns one MPC instance; each lane holds S consecutive control steps in registers
+// (G*S >= control_steps).  Cross-lane work (prefix/suffix scans of the rollout and its adjoint, dot products)
+// is done with warp shuffles; all groups of a warp run in lock step.
+//
+// What it computes follows /root/reference/neo_mpc_planner2/mpc_optimization_server.py ("srv.py"):
+//   objective()            srv.py:204-269      -> Forward::run  (value)  + backward() (analytic gradient)
+//   f_constraint + bounds  srv.py:125-134,157  -> project_step  (exact projection onto box ∩ disc)
+//   minimize(SLSQP)        srv.py:363-364      -> solve_instance (projected L-BFGS; a different algorithm for the same NLP)
+//   optimizer() epilogue   srv.py:358-361,366-402 -> solve_instance tail
+//   collision_check        srv.py:312-347
+//
+// The same header compiles for the host (plain g++, G = 1) so the algorithm can be exercised on machines
+// without a GPU by tests/hostsim; that build is test tooling and is never linked into libneompc.so.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "neompc.h"
+
+#if defined(__CUDACC__)
+#define NEOMPC_HD __host__ __device__ __forceinline__
+#else
+#define NEOMPC_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define NEOMPC_UNROLL _Pragma("unroll")
+#else
+#define NEOMPC_UNROLL
+#endif
+
+// host-only tracing hook for tests/hostsim (compiled out everywhere else)
+#if !defined(NEOMPC_TRACE)
+#define NEOMPC_TRACE(...) ((void)0)
+#endif
+
+namespace neompc {
+
+constexpr int kMaxMemory = 8;          // compile-time cap of L-BFGS pairs
+constexpr int kMaxBacktracks = 12;     // arc-search halvings per iteration
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-handle constants, precomputed on the host (runtime.cu: build_const) and passed by value to the kernels.
+// ---------------------------------------------------------------------------------------------------------
+struct SolverConst {
+  int N;               // control_steps
+  int m;               // L-BFGS memory
+  int max_iter;
+  int disc_only;       // 1: disc lies inside the box -> projection is a radial scaling (README parameters)
+  float dt;            // prediction_horizon / N                      (srv.py:137)
+  float a_trans;       // w_trans / N                                 (srv.py:252)
+  float b_orient;      // w_orient / N
+  float w_ctrl;        // w_control / N                               (srv.py:253-254)
+  float bt_term;       // w_orient * w_terminal                       (srv.py:268)
+  float wt_term;       // w_trans * w_terminal
+  float w_fp;          // w_footprint: N * (1.0^2 * w_footprint / N)  (srv.py:263)
+  float eps2;          // control_smoothing^2
+  float lo[3], hi[3];  // box (srv.py:127-129)
+  float R;             // max_vel_trans (srv.py:158)
+  float acc[3];        // acceleration limits (srv.py:385-391)
+  float lp_gain;       // low_pass_gain (srv.py:366-367)
+  float tol_pg;        // projected-gradient tolerance derived from opt_tolerance
+  float tol_f;         // relative objective-decrease tolerance derived from opt_tolerance
+  // costmap (Costmap2d, srv.py:118)
+  const uint8_t* cells;   // device pointer or nullptr (free space)
+  int W, H;
+  float inv_res;
+  double origin_x, origin_y, inv_res_d;
+  // footprint polygon, robot frame
+  int fp_n;
+  float fp_x[NEOMPC_MAX_FOOTPRINT_VERTICES], fp_y[NEOMPC_MAX_FOOTPRINT_VERTICES];
+  // per-instance state rows: [3*N guess][3 last_control][waiting_time][flags(bits)][goal x,y,yaw][valid]
+  float* state;
+  int state_stride;       // floats per row
+  unsigned state_rows;
+};
+
+// tables derived from (encoding, w_costmap, N): lut_cost[b] = (c==1 ? 1000 : w_costmap) * c^2 / N  (srv.py:247,257-260)
+// lut_flag[b]: bit0 c == 1.0 (lethal), bit1 c >= 0.99 (srv.py:338)
+struct CostTables {
+  const float* cost;      // [257]  entry 256 = out-of-bounds (c = 1.0)
+  const uint8_t* flag;    // [257]
+};
+
+constexpr int kStateExtra = 12;   // floats after the 3N guess in a state row
+NEOMPC_HD int state_stride_for(int n_steps) { return 3 * n_steps + kStateExtra; }
+
+// ---------------------------------------------------------------------------------------------------------
+// lane-group collectives
+// ---------------------------------------------------------------------------------------------------------
+template <int G>
+struct Grp {
+  static NEOMPC_HD float sum(float v) {
+#if defined(__CUDA_ARCH__)
+    NEOMPC_UNROLL
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+#endif
+    return v;
+  }
+  static NEOMPC_HD float max(float v) {
+#if defined(__CUDA_ARCH__)
+    NEOMPC_UNROLL
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+#endif
+    return v;
+  }
+  static NEOMPC_HD int imax(int v) {
+#if defined(__CUDA_ARCH__)
+    NEOMPC_UNROLL
+    for (int o = G / 2; o > 0; o >>= 1) {
+      int t = __shfl_xor_sync(kFullMask, v, o);
+      v = t > v ? t : v;
+    }
+#endif
+    return v;
+  }
+  // sum of v over the lanes of the group that come BEFORE this lane
+  static NEOMPC_HD float excl_prefix(float v, int lg) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) {
+      float incl = v;
+      NEOMPC_UNROLL
+      for (int o = 1; o < G; o <<= 1) {
+        float t = __shfl_up_sync(kFullMask, incl, o, G);
+        if (lg >= o) incl += t;
+      }
+      float ex = __shfl_up_sync(kFullMask, incl, 1, G);
+      return lg > 0 ? ex : 0.0f;
+    }
+#endif
+    (void)v; (void)lg;
+    return 0.0f;
+  }
+  // sum of v over the lanes of the group that come AFTER this lane
+  static NEOMPC_HD float excl_suffix(float v, int lg) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) {
+      float incl = v;
+      NEOMPC_UNROLL
+      for (int o = 1; o < G; o <<= 1) {
+        float t = __shfl_down_sync(kFullMask, incl, o, G);
+        if (lg + o < G) incl += t;
+      }
+      float ex = __shfl_down_sync(kFullMask, incl, 1, G);
+      return lg + 1 < G ? ex : 0.0f;
+    }
+#endif
+    (void)v; (void)lg;
+    return 0.0f;
+  }
+  // true if the predicate holds for any lane of the WARP (all groups of a warp iterate in lock step)
+  static NEOMPC_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(kFullMask, p) != 0;
+#else
+    return p;
+#endif
+  }
+};
+
+NEOMPC_HD void sincos_f(float a, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(a, s, c);
+#else
+  *s = sinf(a);
+  *c = cosf(a);
+#endif
+}
+
+NEOMPC_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Euclidean projection of one control step onto  [lo,hi]^3 ∩ { vx^2 + vy^2 <= R^2 }
+// (bounds srv.py:127-133; disc constraint srv.py:157-158).  omega only sees its interval.
+// ---------------------------------------------------------------------------------------------------------
+NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& om) {
+  om = clampf(om, P.lo[2], P.hi[2]);
+  const float R2 = P.R * P.R;
+  if (P.disc_only) {
+    const float n2 = vx * vx + vy * vy;
+    if (n2 > R2) {
+      const float sc = P.R / sqrtf(n2);
+      vx *= sc;
+      vy *= sc;
+    }
+    return;
+  }
+  const float bx = clampf(vx, P.lo[0], P.hi[0]);
+  const float by = clampf(vy, P.lo[1], P.hi[1]);
+  if (bx * bx + by * by <= R2) {      // box projection already inside the disc
+    vx = bx; vy = by;
+    return;
+  }
+  const float n2 = vx * vx + vy * vy;
+  if (n2 > 0.0f) {
+    const float sc = P.R / sqrtf(n2);
+    const float rx = vx * sc, ry = vy * sc;
+    const float t = 1e-6f;
+    if (rx >= P.lo[0] - t && rx <= P.hi[0] + t && ry >= P.lo[1] - t && ry <= P.hi[1] + t) {
+      vx = clampf(rx, P.lo[0], P.hi[0]);   // disc projection already inside the box
+      vy = clampf(ry, P.lo[1], P.hi[1]);
+      return;
+    }
+  }
+  // Otherwise the projection is a vertex of the feasible region: a box-edge line meeting the circle.
+  float best = 3.4e38f, ox = bx, oy = by;
+  bool found = false;
+  NEOMPC_UNROLL
+  for (int e = 0; e < 4; ++e) {
+    const bool xedge = e < 2;                          // x fixed at a bound, y on the circle
+    const float fixed = xedge ? (e == 0 ? P.lo[0] : P.hi[0]) : (e == 2 ? P.lo[1] : P.hi[1]);
+    const float rem = R2 - fixed * fixed;
+    if (rem < 0.0f) continue;
+    const float root = sqrtf(rem);
+    NEOMPC_UNROLL
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      const float other = sgn ? root : -root;
+      const float lo_o = xedge ? P.lo[1] : P.lo[0];
+      const float hi_o = xedge ? P.hi[1] : P.hi[0];
+      if (other < lo_o || other > hi_o) continue;
+      const float cx = xedge ? fixed : other;
+      const float cy = xedge ? other : fixed;
+      const float d2 = (cx - vx) * (cx - vx) + (cy - vy) * (cy - vy);
+      if (d2 < best) { best = d2; ox = cx; oy = cy; found = true; }
+    }
+  }
+  if (!found) {                                        // degenerate parameters: stay safe
+    const float n = sqrtf(bx * bx + by * by);
+    ox = bx * P.R / n;
+    oy = by * P.R / n;
+  }
+  vx = ox; vy = oy;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-instance constants (hoisted out of objective(): srv.py:207-221)
+// ---------------------------------------------------------------------------------------------------------
+struct Instance {
+  float cx, cy;          // carrot position                    (srv.py:219)
+  float tyaw, fyaw;      // target_yaw, final_yaw              (srv.py:211-212)
+  float v0x, v0y, v0z;   // current velocity                   (srv.py:216-218)
+  float cq, sq;          // cos/sin of pose_yaw_objective      (srv.py:213, hoisted from :234-236)
+  float ct, st;          // cos/sin of the true pose yaw       (srv.py:317)
+  int bx, by;            // cell containing the current position
+  float fx, fy;          // fractional position inside that cell, in cells
+  float jconst;          // terms that do not depend on u: terminal distance (srv.py:266) + footprint (srv.py:262-263)
+};
+
+template <int G, int S>
+struct Forward {
+  float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S];
+
+  // cell lookup for a base-frame offset (x, y) rotated by (cr, sr) from the current position
+  static NEOMPC_HD int cell_of(const SolverConst& P, const Instance& I, float cr, float sr, float x, float y) {
+    if (P.cells == nullptr) return 0 - 1;                      // free space
+    const float gx = I.fx + (cr * x - sr * y) * P.inv_res;
+    const float gy = I.fy + (sr * x + cr * y) * P.inv_res;
+    const int mx = I.bx + (int)floorf(gx);
+    const int my = I.by + (int)floorf(gy);
+    if (mx < 0 || my < 0 || mx >= P.W || my >= P.H) return 256;  // out of bounds
+#if defined(__CUDA_ARCH__)
+    return (int)__ldg(P.cells + (size_t)my * P.W + mx);
+#else
+    return (int)P.cells[(size_t)my * P.W + mx];
+#endif
+  }
+
+  // Rolls the omni-drive model over the horizon (srv.py:230-236) and returns this lane's share of J.
+  // u[j][0..2] = (vx, vy, omega) of step lg*S + j.  smooth: use sqrt(r^2+eps^2) for the control term.
+  NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3],
+                      int lg, bool with_costmap) {
+    const float dt = P.dt;
+    // z_i = dt * sum_{k<=i} omega_k                                               (srv.py:230)
+    float acc = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { acc += u[j][2] * dt; z[j] = acc; }
+    const float zoff = Grp<G>::excl_prefix(acc, lg);
+    float ax = 0.0f, ay = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      z[j] += zoff;
+      sincos_f(z[j], &s[j], &c[j]);
+      dx[j] = (u[j][0] * c[j] - u[j][1] * s[j]) * dt;                              // srv.py:231
+      dy[j] = (u[j][0] * s[j] + u[j][1] * c[j]) * dt;                              // srv.py:232
+      ax += dx[j]; x[j] = ax;
+      ay += dy[j]; y[j] = ay;
+    }
+    const float xoff = Grp<G>::excl_prefix(ax, lg);
+    const float yoff = Grp<G>::excl_prefix(ay, lg);
+    float J = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      x[j] += xoff;
+      y[j] += yoff;
+      const int i = lg * S + j;
+      if (i < P.N) {
+        const float ex = I.cx - x[j], ey = I.cy - y[j], eo = I.tyaw - z[j];
+        J += P.a_trans * (ex * ex + ey * ey) + P.b_orient * (eo * eo);              // srv.py:250-252
+        const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+        J += P.w_ctrl * sqrtf(rx * rx + ry * ry + rz * rz + P.eps2);                // srv.py:253-254 (smoothed)
+        if (with_costmap) {
+          const int cell = cell_of(P, I, I.cq, I.sq, x[j], y[j]);                   // srv.py:246-247 via :234-236
+          if (cell >= 0) J += T.cost[cell];                                         // srv.py:257-260
+        }
+        if (i == P.N - 1) {
+          const float ef = I.fyaw - z[j];
+          J += P.bt_term * (ef * ef);                                               // srv.py:267-268
+        }
+      }
+    }
+    return J;
+  }
+
+  // Adjoint of run(): gradient of the smooth part of J w.r.t. this lane's controls.
+  // Derivation in DESIGN.md ("Analytic gradient"); costmap/footprint terms are piecewise constant -> 0.
+  NEOMPC_HD void backward(const SolverConst& P, const Instance& I, const float (*u)[3], int lg,
+                          float (*g)[3]) const {
+    const float dt = P.dt;
+    float gx[S], gy[S], gz[S];
+    float sx = 0.0f, sy = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = S - 1; j >= 0; --j) {
+      const int i = lg * S + j;
+      const bool on = i < P.N;
+      gx[j] = on ? -2.0f * P.a_trans * (I.cx - x[j]) : 0.0f;
+      gy[j] = on ? -2.0f * P.a_trans * (I.cy - y[j]) : 0.0f;
+      gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
+      if (i == P.N - 1) gz[j] += -2.0f * P.bt_term * (I.fyaw - z[j]);
+      sx += gx[j]; gx[j] = sx;                  // local inclusive suffix sums
+      sy += gy[j]; gy[j] = sy;
+    }
+    const float sxoff = Grp<G>::excl_suffix(sx, lg);
+    const float syoff = Grp<G>::excl_suffix(sy, lg);
+    float sg = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = S - 1; j >= 0; --j) {
+      gx[j] += sxoff;
+      gy[j] += syoff;
+      sg += gz[j] - gx[j] * dy[j] + gy[j] * dx[j];
+      gz[j] = sg;
+    }
+    const float sgoff = Grp<G>::excl_suffix(sg, lg);
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      if (i < P.N) {
+        const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+        const float k = P.w_ctrl / sqrtf(rx * rx + ry * ry + rz * rz + P.eps2);
+        const float kk = (rx * rx + ry * ry + rz * rz + P.eps2) > 0.0f ? k : 0.0f;
+        g[j][0] = dt * (c[j] * gx[j] + s[j] * gy[j]) + kk * rx;
+        g[j][1] = dt * (-s[j] * gx[j] + c[j] * gy[j]) + kk * ry;
+        g[j][2] = dt * (gz[j] + sgoff) + kk * rz;
+      } else {
+        g[j][0] = g[j][1] = g[j][2] = 0.0f;
+      }
+    }
+  }
+};
+
+// value the reference's objective has at u, given the smoothed value: replaces sqrt(r^2+eps^2) by r
+template <int G, int S>
+NEOMPC_HD float unsmooth_correction(const SolverConst& P, const Instance& I, const float (*u)[3], int lg) {
+  float d = 0.0f;
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    if (lg * S + j < P.N) {
+      const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+      const float r2 = rx * rx + ry * ry + rz * rz;
+      d += P.w_ctrl * (sqrtf(r2) - sqrtf(r2 + P.eps2));
+    }
+  }
+  return Grp<G>::sum(d);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Footprint cost at the current pose: nav2 FootprintCollisionChecker::footprintCost restated
+// (vertices -> cells, every edge rasterised with the closed form of nav2's LineIterator, max cell cost).
+// Returns true if the footprint touches a lethal cell or leaves the map (reference test "== 1.0",
+// srv.py:262, :343).  Vertex placement is done in float64 so the cell indices equal the oracle's.
+// ---------------------------------------------------------------------------------------------------------
+template <int G>
+NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, double px, double py, double yaw, int lg) {
+  if (P.cells == nullptr || P.fp_n <= 0) return false;
+  const double cyaw = cos(yaw), syaw = sin(yaw);
+  int lethal = 0;
+  int mx0 = 0, my0 = 0, mxf = 0, myf = 0;
+  for (int v = 0; v <= P.fp_n; ++v) {
+    int mx, my;
+    if (v < P.fp_n) {
+      const double wx = px + ((double)P.fp_x[v] * cyaw - (double)P.fp_y[v] * syaw);
+      const double wy = py + ((double)P.fp_x[v] * syaw + (double)P.fp_y[v] * cyaw);
+      if (wx < P.origin_x || wy < P.origin_y) { lethal = 1; break; }
+      mx = (int)((wx - P.origin_x) * P.inv_res_d);
+      my = (int)((wy - P.origin_y) * P.inv_res_d);
+      if (mx >= P.W || my >= P.H) { lethal = 1; break; }
+      if (v == 0) { mxf = mx; myf = my; mx0 = mx; my0 = my; continue; }
+    } else {
+      mx = mxf; my = myf;                       // closing edge last -> first
+    }
+    // edge (mx0,my0) -> (mx,my): pixel k of nav2's LineIterator
+    const int ddx = mx - mx0, ddy = my - my0;
+    const int adx = ddx < 0 ? -ddx : ddx, ady = ddy < 0 ? -ddy : ddy;
+    const int sxs = ddx >= 0 ? 1 : -1, sys = ddy >= 0 ? 1 : -1;
+    const bool xmaj = adx >= ady;
+    const int den = xmaj ? adx : ady, numadd = xmaj ? ady : adx;
+    for (int k = lg; k <= den; k += G) {
+      const int minor = den > 0 ? (den / 2 + k * numadd) / den : 0;
+      const int cxp = xmaj ? mx0 + k * sxs : mx0 + minor * sxs;
+      const int cyp = xmaj ? my0 + minor * sys : my0 + k * sys;
+      int cell = 256;
+      if (cxp >= 0 && cyp >= 0 && cxp < P.W && cyp < P.H) {
+#if defined(__CUDA_ARCH__)
+        cell = (int)__ldg(P.cells + (size_t)cyp * P.W + cxp);
+#else
+        cell = (int)P.cells[(size_t)cyp * P.W + cxp];
+#endif
+      }
+      lethal |= (T.flag[cell] & 1);
+    }
+    mx0 = mx; my0 = my;
+  }
+  return Grp<G>::imax(lethal) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// History storage for L-BFGS: element e of this lane lives at hist[e * stride] (stride = threads per
+// block in shared memory -> conflict-free; 1 in the host build).
+// Per pair p (0..m-1): [3S floats s][3S floats y][1 float rho]
+// ---------------------------------------------------------------------------------------------------------
+template <int S>
+NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 1); }
+
+struct SolveOut {
+  float cost;
+  unsigned iters, evals, status;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc).
+//   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion; pg = x - Proj(x - g) is the
+//   projected gradient), Armijo backtracking along the projection arc on the TRUE piecewise-constant-
+//   including objective; falls back to a projected-gradient step when the quasi-Newton arc fails.
+// u holds the start point on entry (any point; it is projected) and the solution on exit.
+// `valid` = this group owns an instance; invalid groups only take part in the warp-wide votes/shuffles.
+// ---------------------------------------------------------------------------------------------------------
+template <int S>
+NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
+  float pgmax = 0.0f;
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    float a = u[j][0] - g[j][0], b = u[j][1] - g[j][1], w = u[j][2] - g[j][2];
+    project_step(P, a, b, w);
+    pg[j][0] = u[j][0] - a; pg[j][1] = u[j][1] - b; pg[j][2] = u[j][2] - w;
+    pgmax = fmaxf(pgmax, fmaxf(fabsf(pg[j][0]), fmaxf(fabsf(pg[j][1]), fabsf(pg[j][2]))));
+  }
+  return pgmax;
+}
+
+template <int G, int S>
+NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Instance& I, float (*u)[3],
+                           float* hist, int stride, int lg, bool valid, SolveOut& out) {
+  constexpr int PAIR = 6 * S + 1;
+  const int m = P.m;
+  Forward<G, S> fw;
+  float g[S][3], d[S][3], xt[S][3], pg[S][3];
+
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    if (lg * S + j >= P.N) { u[j][0] = u[j][1] = u[j][2] = 0.0f; }
+    project_step(P, u[j][0], u[j][1], u[j][2]);
+  }
+  for (int e = 0; e < m * PAIR; ++e) hist[e * stride] = 0.0f;
+
+  float f = Grp<G>::sum(fw.run(P, T, I, u, lg, true));
+  fw.backward(P, I, u, lg, g);
+  float pgmax = Grp<G>::max(projected_gradient<S>(P, u, g, pg));
+  unsigned iters = 0, evals = 1, status = NEOMPC_STATUS_MAXITER;
+  int hist_len = 0, head = 0;
+  float gamma = 1.0f;
+  bool active = valid;
+  bool force_pg = true;          // no curvature information yet
+  int small_steps = 0;
+
+  while (true) {
+    // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
+    if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+    if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
+    if (!Grp<G>::warp_any(active)) break;
+
+    // ---- direction: two-loop recursion on the projected gradient
+    const bool use_qn = !force_pg && hist_len > 0;
+    float r[S][3];
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
+    float alpha_k[kMaxMemory];
+    NEOMPC_UNROLL
+    for (int k = 0; k < kMaxMemory; ++k) {
+      alpha_k[k] = 0.0f;
+      if (k < m) {
+        const bool on = use_qn && k < hist_len;
+        int p = head - 1 - k; if (p < 0) p += m;
+        const float* sp = hist + (size_t)(p * PAIR) * stride;
+        const float* yp = sp + (size_t)(3 * S) * stride;
+        float dot = 0.0f;
+        NEOMPC_UNROLL
+        for (int e = 0; e < 3 * S; ++e) dot += sp[(size_t)e * stride] * r[e / 3][e % 3];
+        dot = Grp<G>::sum(dot);
+        const float a = on ? sp[(size_t)(6 * S) * stride] * dot : 0.0f;
+        alpha_k[k] = a;
+        NEOMPC_UNROLL
+        for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
+      }
+    }
+    const float h0 = use_qn ? gamma : 1.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
+    NEOMPC_UNROLL
+    for (int k = kMaxMemory - 1; k >= 0; --k) {
+      if (k < m) {
+        const bool on = use_qn && k < hist_len;
+        int p = head - 1 - k; if (p < 0) p += m;
+        const float* sp = hist + (size_t)(p * PAIR) * stride;
+        const float* yp = sp + (size_t)(3 * S) * stride;
+        float dot = 0.0f;
+        NEOMPC_UNROLL
+        for (int e = 0; e < 3 * S; ++e) dot += yp[(size_t)e * stride] * r[e / 3][e % 3];
+        dot = Grp<G>::sum(dot);
+        const float b = on ? alpha_k[k] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
+        NEOMPC_UNROLL
+        for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] += b * sp[(size_t)e * stride];
+      }
+    }
+    // d = -r; it must be a descent direction for the projected gradient, else restart from -pg
+    float gd = 0.0f, pgn2 = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      NEOMPC_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        d[j][q] = -r[j][q];
+        gd += pg[j][q] * d[j][q];
+        pgn2 += pg[j][q] * pg[j][q];
+      }
+    }
+    gd = Grp<G>::sum(gd);
+    pgn2 = Grp<G>::sum(pgn2);
+    const bool qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
+    float alpha = 1.0f;
+    if (!qn_dir) {
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
+      // first trial moves the largest component by about the velocity range
+      alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+    }
+
+    // ---- Armijo backtracking along the projection arc (all groups of the warp in lock step)
+    bool ls_done = !active, accepted = false;
+    float ft = f;
+    for (int bt = 0; bt < kMaxBacktracks; ++bt) {
+      float gs = 0.0f;
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        xt[j][0] = u[j][0] + alpha * d[j][0];
+        xt[j][1] = u[j][1] + alpha * d[j][1];
+        xt[j][2] = u[j][2] + alpha * d[j][2];
+        project_step(P, xt[j][0], xt[j][1], xt[j][2]);
+        gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
+      }
+      gs = Grp<G>::sum(gs);
+      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg, true));
+      if (!ls_done) {
+        ++evals;
+        ft = ftrial;
+        if (ftrial <= f + 1e-4f * gs && gs < 0.0f) { ls_done = true; accepted = true; }
+      }
+      if (!Grp<G>::warp_any(!ls_done)) break;
+      if (!ls_done) alpha *= 0.5f;
+    }
+    NEOMPC_TRACE("it %u f %.7f pgmax %.3e qn %d alpha %.4g acc %d ft %.7f evals %u hist %d\n", iters, f, pgmax,
+                 (int)qn_dir, alpha, (int)accepted, ft, evals, hist_len);
+    for (int j = 0; j < S; ++j)
+      NEOMPC_TRACE("      u %+.4f %+.4f %+.4f   pg %+.2e %+.2e %+.2e  g %+.2e %+.2e %+.2e\n", u[j][0], u[j][1], u[j][2],
+                   pg[j][0], pg[j][1], pg[j][2], g[j][0], g[j][1], g[j][2]);
+
+    // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
+    float gn[S][3], pgn[S][3];
+    fw.backward(P, I, xt, lg, gn);
+    const float pgmax_n = Grp<G>::max(projected_gradient<S>(P, xt, gn, pgn));
+    if (active) {
+      if (accepted) {
+        // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
+        // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
+        float sy = 0.0f, yy = 0.0f;
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) {
+          NEOMPC_UNROLL
+          for (int q = 0; q < 3; ++q) {
+            const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pg[j][q];
+            sy += sv * yv; yy += yv * yv;
+            d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
+          }
+        }
+        sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy);
+        if (sy > 1e-10f * yy && yy > 0.0f) {
+          float* sp = hist + (size_t)(head * PAIR) * stride;
+          NEOMPC_UNROLL
+          for (int e = 0; e < 3 * S; ++e) {
+            sp[(size_t)e * stride] = d[e / 3][e % 3];
+            sp[(size_t)(3 * S + e) * stride] = r[e / 3][e % 3];
+          }
+          sp[(size_t)(6 * S) * stride] = 1.0f / sy;
+          gamma = sy / yy;
+          head = head + 1 == m ? 0 : head + 1;
+          hist_len = hist_len < m ? hist_len + 1 : m;
+          force_pg = false;
+        }
+        const float df = f - ft;
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) {
+          NEOMPC_UNROLL
+          for (int q = 0; q < 3; ++q) { u[j][q] = xt[j][q]; g[j][q] = gn[j][q]; pg[j][q] = pgn[j][q]; }
+        }
+        f = ft;
+        pgmax = pgmax_n;
+        ++iters;
+        // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
+        if (df <= P.tol_f * fmaxf(1.0f, fabsf(f))) ++small_steps; else small_steps = 0;
+        if (small_steps >= 2) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+      } else if (qn_dir) {
+        hist_len = 0; head = 0; force_pg = true;    // quasi-Newton arc failed: restart with projected gradient
+        ++iters;
+      } else {
+        active = false;                              // projected-gradient arc failed too
+        status = NEOMPC_STATUS_LINESEARCH;
+      }
+    }
+  }
+  out.cost = f;
+  out.iters = iters;
+  out.evals = evals;
+  out.status = status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One optimizer() call (srv.py:349-403) for the instance owned by this lane group.
+// ---------------------------------------------------------------------------------------------------------
+template <int G, int S>
+NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid,
+                              int lg, float* hist, int stride, neompc_response* resp, float* twist, float* plan) {
+  Instance I;
+  I.cx = rq.carrot_x; I.cy = rq.carrot_y;
+  I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
+  I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
+  sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+  sincos_f(rq.pose_yaw, &I.st, &I.ct);
+  I.bx = I.by = 0; I.fx = I.fy = 0.0f;
+  if (P.cells != nullptr) {
+    // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
+    const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
+    const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
+    const double bxd = floor(gx), byd = floor(gy);
+    I.bx = (int)bxd; I.by = (int)byd;
+    I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
+  }
+  const bool fp_hit = valid && footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  {
+    const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
+    I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);        // srv.py:266,268 ; :262-263
+  }
+
+  // ---- per-instance state and the new-goal reset (srv.py:358-361)
+  const bool stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr &&
+                        rq.instance_id < P.state_rows;
+  float* row = stateful ? P.state + (size_t)rq.instance_id * P.state_stride : nullptr;
+  float* tail = stateful ? row + 3 * P.N : nullptr;
+  float last[3] = {0.0f, 0.0f, 0.0f};
+  float waiting = 0.0f;
+  bool latched = false;
+  bool new_goal = true;
+  if (stateful) {
+    new_goal = !(tail[8] != 0.0f && tail[5] == rq.goal_x && tail[6] == rq.goal_y && tail[7] == rq.goal_yaw);
+    waiting = tail[3];
+    latched = tail[4] != 0.0f;
+    if (!new_goal) { last[0] = tail[0]; last[1] = tail[1]; last[2] = tail[2]; }
+    else waiting = 0.0f;
+  }
+  float u[S][3];
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    const int i = lg * S + j;
+    const bool ld = stateful && !new_goal && i < P.N;
+    u[j][0] = ld ? row[3 * i + 0] : 0.0f;
+    u[j][1] = ld ? row[3 * i + 1] : 0.0f;
+    u[j][2] = ld ? row[3 * i + 2] : 0.0f;
+  }
+
+  // ---- the solve (srv.py:363-364)
+  SolveOut so;
+  lbfgs_solve<G, S>(P, T, I, u, hist, stride, lg, valid, so);
+  const float j_true = so.cost + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
+  if (valid && plan != nullptr) {
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      if (i < P.N) { plan[3 * i + 0] = u[j][0]; plan[3 * i + 1] = u[j][1]; plan[3 * i + 2] = u[j][2]; }
+    }
+  }
+
+  // ---- low-pass on the first control, in place (srv.py:366-367)
+  if (lg == 0) {
+    NEOMPC_UNROLL
+    for (int q = 0; q < 3; ++q) u[0][q] = u[0][q] * P.lp_gain + last[q] * (1.0f - P.lp_gain);
+  }
+  // ---- collision_check: re-roll with the TRUE yaw (srv.py:312-347)
+  Forward<G, S> fw;
+  (void)fw.run(P, T, I, u, lg, false);
+  int hit = 0;
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    if (lg * S + j < P.N) {
+      const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
+      if (cell >= 0) hit |= (T.flag[cell] >> 1) & 1;                                  // col >= 0.99, srv.py:338
+    }
+  }
+  hit = Grp<G>::imax(hit);
+  bool collision = latched || hit != 0;
+  float o[3];
+#if defined(__CUDA_ARCH__)
+  o[0] = __shfl_sync(kFullMask, u[0][0], 0, G);
+  o[1] = __shfl_sync(kFullMask, u[0][1], 0, G);
+  o[2] = __shfl_sync(kFullMask, u[0][2], 0, G);
+#else
+  o[0] = u[0][0]; o[1] = u[0][1]; o[2] = u[0][2];
+#endif
+  const float lp0 = o[0], lp1 = o[1], lp2 = o[2];
+  unsigned flags = 0;
+  if (collision || fp_hit) {                                                          // srv.py:374-382
+    o[0] = o[1] = o[2] = 0.0f;
+    flags |= NEOMPC_FLAG_STOPPED;
+    waiting += rq.delta_t;
+    if (waiting >= 3.0f) { collision = false; waiting = 0.0f; }
+  } else {                                                                            // srv.py:385-391
+    NEOMPC_UNROLL
+    for (int q = 0; q < 3; ++q) {
+      const float lim = P.acc[q] * rq.control_interval;
+      o[q] = fmaxf(fminf(o[q], last[q] + lim), last[q] - lim);
+    }
+  }
+  if (collision) flags |= NEOMPC_FLAG_COLLISION;
+  if (fp_hit) flags |= NEOMPC_FLAG_COLLISION_FOOTPRINT;
+  if (new_goal) flags |= NEOMPC_FLAG_NEW_GOAL;
+
+  if (!valid) return;
+  // ---- state: last_control (srv.py:393-395), warm start (srv.py:397-400), old_goal (srv.py:402)
+  if (stateful) {
+    const bool success = so.status != NEOMPC_STATUS_MAXITER;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      if (i < P.N) {
+        // success: plan shifted left by one step, tail = low-passed first control (srv.py:198-202)
+        const int dst = success ? (i == 0 ? P.N - 1 : i - 1) : i;
+        row[3 * dst + 0] = u[j][0]; row[3 * dst + 1] = u[j][1]; row[3 * dst + 2] = u[j][2];
+      }
+    }
+    if (lg == 0) {
+      tail[0] = o[0]; tail[1] = o[1]; tail[2] = o[2];
+      tail[3] = waiting;
+      tail[4] = collision ? 1.0f : 0.0f;
+      tail[5] = rq.goal_x; tail[6] = rq.goal_y; tail[7] = rq.goal_yaw;
+      tail[8] = 1.0f;
+      tail[9] = fp_hit ? 1.0f : 0.0f;
+    }
+  }
+  (void)lp0; (void)lp1; (void)lp2;
+  if (lg == 0) {
+    neompc_response rs;
+    rs.vx = o[0]; rs.vy = o[1]; rs.omega = o[2];
+    rs.cost = j_true;
+    rs.iters = so.iters; rs.evals = so.evals; rs.status = so.status; rs.flags = flags;
+    *resp = rs;
+    if (twist != nullptr) { twist[0] = o[0]; twist[1] = o[1]; twist[2] = o[2]; }
+  }
+}
+
+// objective value (reference J, unsmoothed) and gradient (smoothed objective) at a given u — test hook
+template <int G, int S>
+NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
+                             const float* uin, float* Jout, float* gout) {
+  Instance I;
+  I.cx = rq.carrot_x; I.cy = rq.carrot_y;
+  I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
+  I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
+  sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+  sincos_f(rq.pose_yaw, &I.st, &I.ct);
+  I.bx = I.by = 0; I.fx = I.fy = 0.0f;
+  if (P.cells != nullptr) {
+    const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
+    const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
+    const double bxd = floor(gx), byd = floor(gy);
+    I.bx = (int)bxd; I.by = (int)byd;
+    I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
+  }
+  const bool fp_hit = valid && footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
+  I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);
+  float u[S][3], g[S][3];
+  NEOMPC_UNROLL
+  for (int j = 0; j < S; ++j) {
+    const int i = lg * S + j;
+    const bool ld = valid && i < P.N;
+    u[j][0] = ld ? uin[3 * i + 0] : 0.0f;
+    u[j][1] = ld ? uin[3 * i + 1] : 0.0f;
+    u[j][2] = ld ? uin[3 * i + 2] : 0.0f;
+  }
+  Forward<G, S> fw;
+  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg, true));
+  const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
+  fw.backward(P, I, u, lg, g);
+  if (!valid) return;
+  if (lg == 0) *Jout = jt;
+  if (gout != nullptr) {
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      if (i < P.N) { gout[3 * i + 0] = g[j][0]; gout[3 * i + 1] = g[j][1]; gout[3 * i + 2] = g[j][2]; }
+    }
+  }
+}
+
+}  // namespace neompc

@@ -1,0 +1,114 @@
+// mpc_setup.h — host-side derivation of the solver constants and cost tables from neompc_params
+// (plain C++; shared by the CUDA runtime and by the tests/hostsim tooling).
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mpc_core.cuh"
+
+namespace neompc {
+
+struct HostTables {
+  std::vector<float> cost;     // 257
+  std::vector<uint8_t> flag;   // 257
+};
+
+inline double cell_cost(int encoding, int byte) {
+  // declared costmap semantics (oracle/costmap.py: cost_lut)
+  if (encoding == NEOMPC_ENC_OCCUPANCY) return (byte >= 0 && byte <= 100) ? byte / 100.0 : 0.0;
+  return (byte >= 0 && byte <= 254) ? byte / 254.0 : 0.0;
+}
+
+// lut_cost[b] = (c == 1.0 ? 1000 : w_costmap) * c^2 / N     (srv.py:247, 257-260)
+inline void build_tables(const neompc_params& p, int encoding, HostTables& t) {
+  t.cost.assign(257, 0.0f);
+  t.flag.assign(257, 0);
+  for (int b = 0; b <= 256; ++b) {
+    const double c = b == 256 ? 1.0 : cell_cost(encoding, b);
+    const double cc = c * c;
+    const double v = (c == 1.0) ? cc * 1000.0 / p.control_steps : (double)p.w_costmap * cc / p.control_steps;
+    t.cost[b] = (float)v;
+    t.flag[b] = (uint8_t)((c == 1.0 ? 1 : 0) | (c >= 0.99 ? 2 : 0));
+  }
+}
+
+inline bool validate_params(const neompc_params& p, std::string& err) {
+  if (p.control_steps < 1 || p.control_steps > NEOMPC_MAX_CONTROL_STEPS) {
+    err = "control_steps must be in 1.." + std::to_string(NEOMPC_MAX_CONTROL_STEPS);
+    return false;
+  }
+  if (!(p.prediction_horizon > 0.0f)) { err = "prediction_horizon must be > 0"; return false; }
+  if (!(p.max_vel_trans > 0.0f)) { err = "max_vel_trans must be > 0"; return false; }
+  if (!(p.min_vel_x <= p.max_vel_x && p.min_vel_y <= p.max_vel_y && p.min_vel_theta <= p.max_vel_theta)) {
+    err = "min_vel_* must not exceed max_vel_*";
+    return false;
+  }
+  // the feasible set box ∩ disc must be non-empty: the box point closest to the origin lies in the disc
+  const float nx = fminf(fmaxf(0.0f, p.min_vel_x), p.max_vel_x);
+  const float ny = fminf(fmaxf(0.0f, p.min_vel_y), p.max_vel_y);
+  if (nx * nx + ny * ny > p.max_vel_trans * p.max_vel_trans) {
+    err = "velocity box and max_vel_trans disc do not intersect";
+    return false;
+  }
+  if (p.lbfgs_memory < 0 || p.lbfgs_memory > kMaxMemory) { err = "lbfgs_memory must be 0..8"; return false; }
+  if (p.max_iterations < 0) { err = "max_iterations must be >= 0"; return false; }
+  if (!(p.opt_tolerance > 0.0f)) { err = "opt_tolerance must be > 0"; return false; }
+  const int g = p.lanes_per_instance;
+  if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) {
+    err = "lanes_per_instance must be 0 (auto) or a power of two <= 32";
+    return false;
+  }
+  return true;
+}
+
+// Solver tolerances derived from the reference's opt_tolerance (SLSQP's ftol there).  See DESIGN.md
+// "Meaning of opt_tolerance": the projected-gradient sup-norm must fall below kPgScale * opt_tolerance, or the
+// objective must stop decreasing by more than kFScale * opt_tolerance (relative) twice in a row.
+constexpr float kPgScale = 0.05f;
+constexpr float kFScale = 1e-3f;
+
+inline void build_const(const neompc_params& p, SolverConst& c) {
+  std::memset(&c, 0, sizeof(c));
+  const int N = p.control_steps;
+  c.N = N;
+  c.m = p.lbfgs_memory > 0 ? p.lbfgs_memory : 5;
+  c.max_iter = p.max_iterations > 0 ? p.max_iterations : 100;
+  c.dt = p.prediction_horizon / (float)N;
+  c.a_trans = p.w_trans / (float)N;
+  c.b_orient = p.w_orient / (float)N;
+  c.w_ctrl = p.w_control / (float)N;
+  c.bt_term = p.w_orient * p.w_terminal;
+  c.wt_term = p.w_trans * p.w_terminal;
+  c.w_fp = p.w_footprint;
+  const float eps = p.control_smoothing > 0.0f ? p.control_smoothing : 1e-2f;
+  c.eps2 = eps * eps;
+  c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;
+  c.hi[0] = p.max_vel_x; c.hi[1] = p.max_vel_y; c.hi[2] = p.max_vel_theta;
+  c.R = p.max_vel_trans;
+  c.disc_only = (p.max_vel_trans <= fminf(fminf(-p.min_vel_x, p.max_vel_x), fminf(-p.min_vel_y, p.max_vel_y))) ? 1 : 0;
+  c.acc[0] = p.acc_x_limit; c.acc[1] = p.acc_y_limit; c.acc[2] = p.acc_theta_limit;
+  c.lp_gain = p.low_pass_gain;
+  c.tol_pg = kPgScale * p.opt_tolerance;
+  c.tol_f = kFScale * p.opt_tolerance;
+  c.cells = nullptr;
+  c.state = nullptr;
+  c.state_stride = state_stride_for(N);
+  c.state_rows = 0;
+}
+
+// lanes-per-instance G and steps-per-lane S for a horizon of n steps (G*S >= n, S <= 6)
+inline void choose_tiling(int n_steps, int lanes_override, int* G, int* S) {
+  int g = lanes_override;
+  if (g <= 0) {
+    g = 1;
+    while ((n_steps + g - 1) / g > 3 && g < 32) g <<= 1;       // default: at most 3 steps per lane
+  }
+  while ((n_steps + g - 1) / g > 6 && g < 32) g <<= 1;         // S is instantiated up to 6
+  *G = g;
+  *S = (n_steps + g - 1) / g;
+}
+
+}  // namespace neompc

@@ -1,0 +1,489 @@
+// runtime.cu — the C ABI of libneompc (include/neompc.h): handle, device buffers, streams, dispatch.
+// Replaces the ROS service hop between NeoMpcPlanner::computeVelocityCommands (reference src/NeoMpcPlanner.cpp:240-252)
+// and MpcOptimizationServer.optimizer (reference neo_mpc_planner2/mpc_optimization_server.py:349-403).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "mpc_setup.h"
+
+using namespace neompc;
+
+struct neompc_handle {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  neompc_params params{};
+  SolverConst c{};
+  HostTables tab;
+  int encoding = NEOMPC_ENC_OCCUPANCY;
+  int G = 1, S = 1;
+  float* d_lut_cost = nullptr;
+  uint8_t* d_lut_flag = nullptr;
+  uint8_t* d_cells = nullptr;
+  size_t cells_cap = 0;
+  float* d_state = nullptr;
+  unsigned state_rows = 0;
+  // staging for the host-buffer entry points
+  neompc_request* d_reqs = nullptr;
+  neompc_response* d_resp = nullptr;
+  float* d_plan = nullptr;
+  neompc_optimizer_request* d_msgs = nullptr;
+  size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int fail(neompc_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int cuda_fail(neompc_handle* h, cudaError_t e, const char* what) {
+  return fail(h, NEOMPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define NEOMPC_CUDA(h, call)                                  \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);  \
+  } while (0)
+
+int upload_tables(neompc_handle* h) {
+  build_tables(h->params, h->encoding, h->tab);
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_cost, h->tab.cost.data(), 257 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_flag, h->tab.flag.data(), 257, cudaMemcpyHostToDevice, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+// everything in SolverConst that does not come from neompc_params survives a parameter update
+void rebuild_const(neompc_handle* h) {
+  const SolverConst old = h->c;
+  build_const(h->params, h->c);
+  h->c.cells = old.cells; h->c.W = old.W; h->c.H = old.H;
+  h->c.inv_res = old.inv_res; h->c.inv_res_d = old.inv_res_d;
+  h->c.origin_x = old.origin_x; h->c.origin_y = old.origin_y;
+  h->c.fp_n = old.fp_n;
+  std::memcpy(h->c.fp_x, old.fp_x, sizeof(old.fp_x));
+  std::memcpy(h->c.fp_y, old.fp_y, sizeof(old.fp_y));
+  h->c.state = h->d_state;
+  h->c.state_rows = h->state_rows;
+  choose_tiling(h->params.control_steps, h->params.lanes_per_instance, &h->G, &h->S);
+}
+
+int ensure_staging(neompc_handle* h, size_t n, bool want_plan, bool want_msgs) {
+  if (n > h->cap_reqs) {
+    if (h->d_reqs) cudaFree(h->d_reqs);
+    if (h->d_resp) cudaFree(h->d_resp);
+    h->d_reqs = nullptr; h->d_resp = nullptr; h->cap_reqs = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_reqs, n * sizeof(neompc_request)));
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_resp, n * sizeof(neompc_response)));
+    h->cap_reqs = n;
+  }
+  const size_t plan_floats = n * 3 * (size_t)h->params.control_steps;
+  if (want_plan && plan_floats > h->cap_plan) {
+    if (h->d_plan) cudaFree(h->d_plan);
+    h->d_plan = nullptr; h->cap_plan = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_plan, plan_floats * sizeof(float)));
+    h->cap_plan = plan_floats;
+  }
+  if (want_msgs && n > h->cap_msgs) {
+    if (h->d_msgs) cudaFree(h->d_msgs);
+    h->d_msgs = nullptr; h->cap_msgs = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_msgs, n * sizeof(neompc_optimizer_request)));
+    h->cap_msgs = n;
+  }
+  return NEOMPC_OK;
+}
+
+cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
+  switch (h->G) {
+    case 1: return launch_g1(eval, h->S, a);
+    case 2: return launch_g2(eval, h->S, a);
+    case 4: return launch_g4(eval, h->S, a);
+    case 8: return launch_g8(eval, h->S, a);
+    case 16: return launch_g16(eval, h->S, a);
+    case 32: return launch_g32(eval, h->S, a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// euler_from_quaternion yaw (reference mpc_optimization_server.py:176-178), float64 like the reference
+__device__ __forceinline__ double yaw_of(double x, double y, double z, double w) {
+  return atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z));
+}
+
+// Optimizer.Request (float64, quaternions) -> neompc_request (float32, yaws).  One thread per message.
+__global__ void pack_kernel(const neompc_optimizer_request* __restrict__ msgs, unsigned n,
+                            neompc_request* __restrict__ reqs) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const neompc_optimizer_request& m = msgs[i];
+  neompc_request r;
+  r.vel_x = (float)m.current_vel[0];                                  // srv.py:216
+  r.vel_y = (float)m.current_vel[1];                                  // srv.py:217
+  r.vel_theta = (float)m.current_vel[5];                              // srv.py:218
+  r.carrot_x = (float)m.carrot_pose[0];
+  r.carrot_y = (float)m.carrot_pose[1];
+  r.carrot_yaw = (float)yaw_of(m.carrot_pose[3], m.carrot_pose[4], m.carrot_pose[5], m.carrot_pose[6]);   // srv.py:211
+  r.goal_x = (float)m.goal_pose[0];
+  r.goal_y = (float)m.goal_pose[1];
+  r.goal_yaw = (float)yaw_of(m.goal_pose[3], m.goal_pose[4], m.goal_pose[5], m.goal_pose[6]);             // srv.py:212
+  r.pose_x = (float)m.current_pose[0];
+  r.pose_y = (float)m.current_pose[1];
+  r.pose_yaw = (float)yaw_of(m.current_pose[3], m.current_pose[4], m.current_pose[5], m.current_pose[6]); // srv.py:317
+  // the reference takes w from the GOAL pose here (srv.py:213)
+  r.pose_yaw_objective = (float)yaw_of(m.current_pose[3], m.current_pose[4], m.current_pose[5], m.goal_pose[6]);
+  r.control_interval = (float)m.control_interval;
+  r.delta_t = (float)fmin(m.delta_t, 3.0e38);
+  r.instance_id = m.instance_id;
+  reqs[i] = r;
+}
+
+__global__ void reset_rows_kernel(float* state, int stride, const uint32_t* ids, unsigned n, unsigned rows) {
+  const unsigned i = blockIdx.x;
+  if (i >= n) return;
+  const uint32_t id = ids[i];
+  if (id >= rows) return;
+  for (int k = threadIdx.x; k < stride; k += blockDim.x) state[(size_t)id * stride + k] = 0.0f;
+}
+
+int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
+                    float* d_twist, float* d_plan, cudaStream_t s) {
+  if (n == 0) return NEOMPC_OK;
+  if (n > 0xFFFFFFF0ull) return fail(h, NEOMPC_ERR_INVALID, "batch too large");
+  LaunchArgs a{};
+  a.P = h->c;
+  a.lut_cost = h->d_lut_cost;
+  a.lut_flag = h->d_lut_flag;
+  a.reqs = d_reqs;
+  a.n = (unsigned)n;
+  a.out = d_out;
+  a.twist = d_twist;
+  a.plan = d_plan;
+  a.stream = s;
+  cudaError_t e = dispatch(h, false, a);
+  if (e != cudaSuccess) return cuda_fail(h, e, "solve kernel launch");
+  h->launches += 1;
+  return NEOMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int neompc_version(void) { return NEOMPC_VERSION; }
+
+int neompc_abi_sizes(size_t out[4]) {
+  if (!out) return NEOMPC_ERR_INVALID;
+  out[0] = sizeof(neompc_request);
+  out[1] = sizeof(neompc_response);
+  out[2] = sizeof(neompc_params);
+  out[3] = sizeof(neompc_optimizer_request);
+  return NEOMPC_OK;
+}
+
+const char* neompc_last_error(const neompc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int neompc_create(const neompc_params* params, int device, neompc_handle** out) {
+  if (!params || !out) return fail(nullptr, NEOMPC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::string err;
+  if (!validate_params(*params, err)) return fail(nullptr, NEOMPC_ERR_INVALID, err);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, NEOMPC_ERR_NO_DEVICE,
+                std::string("no CUDA device available (libneompc has no CPU fallback): ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= count) return fail(nullptr, NEOMPC_ERR_NO_DEVICE, "device ordinal out of range");
+  neompc_handle* h = new (std::nothrow) neompc_handle();
+  if (!h) return fail(nullptr, NEOMPC_ERR_INVALID, "out of host memory");
+  h->device = device;
+  h->params = *params;
+#define CREATE_CUDA(call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      g_create_error = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      neompc_destroy(h);                                                                    \
+      return NEOMPC_ERR_CUDA;                                                               \
+    }                                                                                       \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(device));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaMalloc(&h->d_lut_cost, 257 * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_lut_flag, 260));
+#undef CREATE_CUDA
+  build_const(h->params, h->c);
+  rebuild_const(h);
+  int rc = upload_tables(h);
+  if (rc != NEOMPC_OK) { g_create_error = h->err; neompc_destroy(h); return rc; }
+  *out = h;
+  return NEOMPC_OK;
+}
+
+int neompc_destroy(neompc_handle* h) {
+  if (!h) return NEOMPC_OK;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
+  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
+  delete h;
+  return NEOMPC_OK;
+}
+
+int neompc_set_params(neompc_handle* h, const neompc_params* params) {
+  if (!h || !params) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  std::string err;
+  if (!validate_params(*params, err)) return fail(h, NEOMPC_ERR_INVALID, err);
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  const bool steps_changed = params->control_steps != h->params.control_steps;
+  h->params = *params;
+  if (steps_changed && h->d_state) {           // rows have a different layout now: start over (srv.py never resizes either)
+    const unsigned rows = h->state_rows;
+    cudaFree(h->d_state);
+    h->d_state = nullptr; h->state_rows = 0;
+    rebuild_const(h);
+    int rc = neompc_reserve_instances(h, rows);
+    if (rc != NEOMPC_OK) return rc;
+  }
+  rebuild_const(h);
+  return upload_tables(h);
+}
+
+int neompc_get_params(const neompc_handle* h, neompc_params* out) {
+  if (!h || !out) return NEOMPC_ERR_INVALID;
+  *out = h->params;
+  return NEOMPC_OK;
+}
+
+static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_device, uint32_t width, uint32_t height,
+                              double resolution, double origin_x, double origin_y, int encoding) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  if (encoding != NEOMPC_ENC_OCCUPANCY && encoding != NEOMPC_ENC_NAV2_RAW)
+    return fail(h, NEOMPC_ERR_INVALID, "unknown costmap encoding");
+  if (cells == nullptr) {                      // free space
+    h->c.cells = nullptr; h->c.W = h->c.H = 0;
+    return NEOMPC_OK;
+  }
+  if (width == 0 || height == 0 || width > 65535u || height > 65535u || !(resolution > 0.0))
+    return fail(h, NEOMPC_ERR_INVALID, "bad costmap geometry");
+  const size_t bytes = (size_t)width * height;
+  if (bytes > h->cells_cap) {
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_cells) cudaFree(h->d_cells);
+    h->d_cells = nullptr; h->cells_cap = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_cells, bytes));
+    h->cells_cap = bytes;
+  }
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_cells, cells, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                 h->stream));
+  h->c.cells = h->d_cells;
+  h->c.W = (int)width; h->c.H = (int)height;
+  h->c.inv_res_d = 1.0 / resolution;
+  h->c.inv_res = (float)(1.0 / resolution);
+  h->c.origin_x = origin_x; h->c.origin_y = origin_y;
+  if (encoding != h->encoding) {
+    h->encoding = encoding;
+    return upload_tables(h);
+  }
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+int neompc_set_costmap(neompc_handle* h, const uint8_t* cells, uint32_t width, uint32_t height, double resolution,
+                       double origin_x, double origin_y, int encoding) {
+  return set_costmap_common(h, cells, false, width, height, resolution, origin_x, origin_y, encoding);
+}
+
+int neompc_set_costmap_device(neompc_handle* h, const uint8_t* d_cells, uint32_t width, uint32_t height,
+                              double resolution, double origin_x, double origin_y, int encoding) {
+  return set_costmap_common(h, d_cells, true, width, height, resolution, origin_x, origin_y, encoding);
+}
+
+int neompc_set_footprint(neompc_handle* h, const float* xy, int n_vertices) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  if (n_vertices < 0 || n_vertices > NEOMPC_MAX_FOOTPRINT_VERTICES || (n_vertices > 0 && !xy))
+    return fail(h, NEOMPC_ERR_INVALID, "footprint must have 0..16 vertices");
+  h->c.fp_n = n_vertices;
+  for (int i = 0; i < n_vertices; ++i) { h->c.fp_x[i] = xy[2 * i]; h->c.fp_y[i] = xy[2 * i + 1]; }
+  return NEOMPC_OK;
+}
+
+int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  if (n_instances <= h->state_rows) return NEOMPC_OK;
+  const int stride = state_stride_for(h->params.control_steps);
+  float* fresh = nullptr;
+  NEOMPC_CUDA(h, cudaMalloc(&fresh, (size_t)n_instances * stride * sizeof(float)));
+  NEOMPC_CUDA(h, cudaMemsetAsync(fresh, 0, (size_t)n_instances * stride * sizeof(float), h->stream));
+  if (h->d_state) {
+    NEOMPC_CUDA(h, cudaMemcpyAsync(fresh, h->d_state, (size_t)h->state_rows * stride * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, h->stream));
+  }
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->d_state) cudaFree(h->d_state);
+  h->d_state = fresh;
+  h->state_rows = n_instances;
+  h->c.state = h->d_state;
+  h->c.state_rows = h->state_rows;
+  h->c.state_stride = stride;
+  return NEOMPC_OK;
+}
+
+int neompc_reset_state(neompc_handle* h, const uint32_t* ids, size_t n) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  if (!h->d_state) return NEOMPC_OK;
+  const int stride = h->c.state_stride;
+  if (ids == nullptr) {
+    NEOMPC_CUDA(h, cudaMemsetAsync(h->d_state, 0, (size_t)h->state_rows * stride * sizeof(float), h->stream));
+  } else if (n > 0) {
+    uint32_t* d_ids = nullptr;
+    NEOMPC_CUDA(h, cudaMalloc(&d_ids, n * sizeof(uint32_t)));
+    NEOMPC_CUDA(h, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    reset_rows_kernel<<<(unsigned)n, 64, 0, h->stream>>>(h->d_state, stride, d_ids, (unsigned)n, h->state_rows);
+    h->launches += 1;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_ids);
+    if (e != cudaSuccess) return cuda_fail(h, e, "reset_state");
+    return NEOMPC_OK;
+  }
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+int neompc_get_state(neompc_handle* h, uint32_t id, float* initial_guess, float last_control[3], float* waiting_time,
+                     uint32_t* flags) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  if (id >= h->state_rows) return fail(h, NEOMPC_ERR_STATE, "instance id beyond reserved capacity");
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  const int stride = h->c.state_stride;
+  std::vector<float> row(stride);
+  NEOMPC_CUDA(h, cudaMemcpyAsync(row.data(), h->d_state + (size_t)id * stride, stride * sizeof(float),
+                                 cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int n3 = 3 * h->params.control_steps;
+  if (initial_guess) std::memcpy(initial_guess, row.data(), n3 * sizeof(float));
+  if (last_control) std::memcpy(last_control, row.data() + n3, 3 * sizeof(float));
+  if (waiting_time) *waiting_time = row[n3 + 3];
+  if (flags) *flags = (row[n3 + 4] != 0.0f ? NEOMPC_FLAG_COLLISION : 0) |
+                      (row[n3 + 9] != 0.0f ? NEOMPC_FLAG_COLLISION_FOOTPRINT : 0);
+  return NEOMPC_OK;
+}
+
+int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
+                              float* d_twist_or_null, float* d_plan_or_null, void* stream) {
+  if (!h || (n > 0 && (!d_reqs || !d_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  return do_solve_device(h, d_reqs, n, d_out, d_twist_or_null, d_plan_or_null, s);
+}
+
+int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, neompc_response* out,
+                       float* plan_or_null) {
+  if (!h || (n > 0 && (!reqs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h, n, plan_or_null != nullptr, false);
+  if (rc != NEOMPC_OK) return rc;
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs, reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream));
+  rc = do_solve_device(h, h->d_reqs, n, h->d_resp, nullptr, plan_or_null ? h->d_plan : nullptr, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  NEOMPC_CUDA(h, cudaMemcpyAsync(out, h->d_resp, n * sizeof(neompc_response), cudaMemcpyDeviceToHost, h->stream));
+  if (plan_or_null)
+    NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null, h->d_plan, n * 3 * (size_t)h->params.control_steps * sizeof(float),
+                                   cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n, neompc_request* d_reqs,
+                         void* stream) {
+  if (!h || (n > 0 && (!d_msgs || !d_reqs))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_msgs, (unsigned)n, d_reqs);
+  NEOMPC_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return NEOMPC_OK;
+}
+
+int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, size_t n, neompc_response* out,
+                      float* plan_or_null) {
+  if (!h || (n > 0 && (!msgs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h, n, plan_or_null != nullptr, true);
+  if (rc != NEOMPC_OK) return rc;
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_msgs, msgs, n * sizeof(neompc_optimizer_request), cudaMemcpyHostToDevice, h->stream));
+  rc = neompc_pack_requests(h, h->d_msgs, n, h->d_reqs, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  rc = do_solve_device(h, h->d_reqs, n, h->d_resp, nullptr, plan_or_null ? h->d_plan : nullptr, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  NEOMPC_CUDA(h, cudaMemcpyAsync(out, h->d_resp, n * sizeof(neompc_response), cudaMemcpyDeviceToHost, h->stream));
+  if (plan_or_null)
+    NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null, h->d_plan, n * 3 * (size_t)h->params.control_steps * sizeof(float),
+                                   cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const float* u, size_t n, float* J,
+                          float* grad_or_null) {
+  if (!h || (n > 0 && (!reqs || !u || !J))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  const size_t n3 = n * 3 * (size_t)h->params.control_steps;
+  int rc = ensure_staging(h, n, true, false);
+  if (rc != NEOMPC_OK) return rc;
+  float *d_u = nullptr, *d_J = nullptr;
+  NEOMPC_CUDA(h, cudaMalloc(&d_u, n3 * sizeof(float)));
+  cudaError_t e = cudaMalloc(&d_J, n * sizeof(float));
+  if (e != cudaSuccess) { cudaFree(d_u); return cuda_fail(h, e, "cudaMalloc"); }
+  LaunchArgs a{};
+  a.P = h->c; a.lut_cost = h->d_lut_cost; a.lut_flag = h->d_lut_flag;
+  a.reqs = h->d_reqs; a.n = (unsigned)n; a.u = d_u; a.J = d_J; a.grad = grad_or_null ? h->d_plan : nullptr;
+  a.stream = h->stream;
+  e = cudaMemcpyAsync(h->d_reqs, reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u, n3 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) { e = dispatch(h, true, a); h->launches += 1; }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(J, d_J, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && grad_or_null)
+    e = cudaMemcpyAsync(grad_or_null, h->d_plan, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_u); cudaFree(d_J);
+  if (e != cudaSuccess) return cuda_fail(h, e, "eval_objective");
+  return NEOMPC_OK;
+}
+
+uint64_t neompc_launch_count(const neompc_handle* h) { return h ? h->launches : 0; }
+
+int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* steps_per_lane) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  if (lanes_per_instance) *lanes_per_instance = h->G;
+  if (steps_per_lane) *steps_per_lane = h->S;
+  return NEOMPC_OK;
+}
+
+int neompc_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return NEOMPC_ERR_INVALID;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? NEOMPC_OK : NEOMPC_ERR_CUDA;
+}
+
+int neompc_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NEOMPC_OK : NEOMPC_ERR_CUDA; }
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""BatchSolver — thin Python handle on libneompc (the C ABI does the work; see include/neompc.h).
+
+Host-side mirror of what the reference's server object owns: parameters (srv.py:49-103), the costmap
+(srv.py:118), the footprint (srv.py:154-155) and the per-instance state of ``optimizer()`` (srv.py:349-403).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .abi import (REQUEST_DTYPE, RESPONSE_DTYPE, PARAMS_DTYPE, MSG_DTYPE, ENC_OCCUPANCY, params_record)
+
+NeompcError = _lib.NeompcError
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class BatchSolver:
+    def __init__(self, params=None, device: int = 0, **over):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.params = params_record(params, **over)
+        rc = self._lib.neompc_create(_ptr(self.params), int(device), ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._lib.neompc_last_error(None).decode()
+            self._h = ctypes.c_void_p()
+            raise NeompcError(f"neompc_create failed ({rc}): {msg}")
+        self.device = int(device)
+        self.control_steps = int(self.params["control_steps"])
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NeompcError(f"{what} failed ({rc}): {self._lib.neompc_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.neompc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ environment
+    def set_params(self, params=None, **over):
+        rec = params_record(params if params is not None else
+                            {k: self.params[k].item() for k in self.params.dtype.names if k != "reserved"}, **over)
+        self._check(self._lib.neompc_set_params(self._h, _ptr(rec)), "neompc_set_params")
+        self.params = rec
+        self.control_steps = int(rec["control_steps"])
+
+    def set_costmap(self, cells, resolution, origin_x, origin_y, encoding=ENC_OCCUPANCY):
+        if cells is None:
+            self._check(self._lib.neompc_set_costmap(self._h, None, 0, 0, 1.0, 0.0, 0.0, encoding), "neompc_set_costmap")
+            return
+        cells = np.ascontiguousarray(cells)
+        if cells.dtype == np.int8:
+            cells = cells.view(np.uint8)
+        if cells.dtype != np.uint8 or cells.ndim != 2:
+            raise ValueError("cells must be uint8/int8 [H, W]")
+        h, w = cells.shape
+        self._check(self._lib.neompc_set_costmap(self._h, _ptr(cells), w, h, float(resolution), float(origin_x),
+                                                 float(origin_y), int(encoding)), "neompc_set_costmap")
+
+    def set_costmap_device(self, cells_tensor, resolution, origin_x, origin_y, encoding=ENC_OCCUPANCY):
+        h, w = cells_tensor.shape
+        self._check(self._lib.neompc_set_costmap_device(self._h, ctypes.c_void_p(cells_tensor.data_ptr()), w, h,
+                                                        float(resolution), float(origin_x), float(origin_y),
+                                                        int(encoding)), "neompc_set_costmap_device")
+
+    def set_footprint(self, xy):
+        xy = np.ascontiguousarray(np.asarray(xy, dtype=np.float32).reshape(-1, 2))
+        self._check(self._lib.neompc_set_footprint(self._h, _ptr(xy), len(xy)), "neompc_set_footprint")
+
+    def load_workload(self, wl):
+        if wl.cells is not None:
+            self.set_costmap(wl.cells, wl.resolution, wl.origin_x, wl.origin_y, wl.encoding)
+        else:
+            self.set_costmap(None, 1.0, 0.0, 0.0)
+        self.set_footprint(wl.footprint)
+
+    # ------------------------------------------------------------------ per-instance state
+    def reserve_instances(self, n):
+        self._check(self._lib.neompc_reserve_instances(self._h, int(n)), "neompc_reserve_instances")
+
+    def reset_state(self, ids=None):
+        if ids is None:
+            self._check(self._lib.neompc_reset_state(self._h, None, 0), "neompc_reset_state")
+        else:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+            self._check(self._lib.neompc_reset_state(self._h, _ptr(ids), len(ids)), "neompc_reset_state")
+
+    def get_state(self, instance_id):
+        guess = np.zeros(3 * self.control_steps, np.float32)
+        last = np.zeros(3, np.float32)
+        wait = ctypes.c_float()
+        flags = ctypes.c_uint32()
+        self._check(self._lib.neompc_get_state(self._h, int(instance_id), _ptr(guess), _ptr(last),
+                                               ctypes.byref(wait), ctypes.byref(flags)), "neompc_get_state")
+        return dict(initial_guess=guess, last_control=last, waiting_time=wait.value, flags=flags.value)
+
+    # ------------------------------------------------------------------ the hot path
+    def solve(self, reqs, want_plan=False, out=None, plan_out=None):
+        """Host buffers in, host buffers out (neompc_solve_batch)."""
+        reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)
+        n = len(reqs)
+        if out is None:
+            out = np.empty(n, RESPONSE_DTYPE)
+        plan = None
+        if want_plan:
+            plan = plan_out if plan_out is not None else np.empty((n, 3 * self.control_steps), np.float32)
+        self._check(self._lib.neompc_solve_batch(self._h, _ptr(reqs), n, _ptr(out), _ptr(plan)), "neompc_solve_batch")
+        return (out, plan) if want_plan else out
+
+    def solve_raw(self, reqs_ptr, n, out_ptr, plan_ptr=None):
+        """neompc_solve_batch on raw host addresses (e.g. pinned torch tensors)."""
+        self._check(self._lib.neompc_solve_batch(self._h, ctypes.c_void_p(reqs_ptr), int(n), ctypes.c_void_p(out_ptr),
+                                                 ctypes.c_void_p(plan_ptr) if plan_ptr else None), "neompc_solve_batch")
+
+    def solve_device(self, d_reqs, n, d_out, d_twist=None, d_plan=None, stream=None):
+        """Device pointers (ints) in and out, asynchronous on `stream` (a cudaStream_t as int; None = handle stream)."""
+        self._check(self._lib.neompc_solve_batch_device(
+            self._h, ctypes.c_void_p(d_reqs), int(n), ctypes.c_void_p(d_out),
+            ctypes.c_void_p(d_twist) if d_twist else None, ctypes.c_void_p(d_plan) if d_plan else None,
+            ctypes.c_void_p(stream) if stream else None), "neompc_solve_batch_device")
+
+    def solve_msgs(self, msgs, want_plan=False):
+        msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
+        n = len(msgs)
+        out = np.empty(n, RESPONSE_DTYPE)
+        plan = np.empty((n, 3 * self.control_steps), np.float32) if want_plan else None
+        self._check(self._lib.neompc_solve_msgs(self._h, _ptr(msgs), n, _ptr(out), _ptr(plan)), "neompc_solve_msgs")
+        return (out, plan) if want_plan else out
+
+    def pack_requests_device(self, d_msgs, n, d_reqs, stream=None):
+        self._check(self._lib.neompc_pack_requests(self._h, ctypes.c_void_p(d_msgs), int(n), ctypes.c_void_p(d_reqs),
+                                                   ctypes.c_void_p(stream) if stream else None), "neompc_pack_requests")
+
+    def eval_objective(self, reqs, u, want_grad=True):
+        reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)
+        n = len(reqs)
+        u = np.ascontiguousarray(u, dtype=np.float32).reshape(n, 3 * self.control_steps)
+        J = np.empty(n, np.float32)
+        g = np.empty_like(u) if want_grad else None
+        self._check(self._lib.neompc_eval_objective(self._h, _ptr(reqs), _ptr(u), n, _ptr(J), _ptr(g)),
+                    "neompc_eval_objective")
+        return (J, g) if want_grad else J
+
+    @property
+    def launch_count(self):
+        return int(self._lib.neompc_launch_count(self._h))
+
+    @property
+    def tiling(self):
+        g, s = ctypes.c_int(), ctypes.c_int()
+        self._lib.neompc_get_tiling(self._h, ctypes.byref(g), ctypes.byref(s))
+        return g.value, s.value

@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/neompc.h declares,
+its records have the sizes the numpy mirrors assume, and it refuses to run without a CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from neo_mpc_planner2_b200 import _lib, abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    header = open(os.path.join(ROOT, "include", "neompc.h")).read()
+    declared = set(re.findall(r"\b(neompc_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_record_sizes(lib):
+    sz = (ctypes.c_size_t * 4)()
+    assert lib.neompc_abi_sizes(sz) == 0
+    assert list(sz) == [abi.REQUEST_DTYPE.itemsize, abi.RESPONSE_DTYPE.itemsize, abi.PARAMS_DTYPE.itemsize,
+                        abi.MSG_DTYPE.itemsize] == [64, 32, 128, 240]
+    assert lib.neompc_version() == 100
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from neo_mpc_planner2_b200.solver import BatchSolver, NeompcError
+    with pytest.raises(NeompcError, match="no CPU fallback"):
+        BatchSolver(abi.README_SAMPLE)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "neo_mpc_planner2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "scipy.optimize" not in src, f
