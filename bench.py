@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -146,7 +146,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -158,7 +158,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=1.0)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
@@ -202,7 +202,8 @@ def run_ours(args):
     d_twist = torch.empty((n, 3), dtype=torch.float32, device=dev)
     d_all = torch.empty((world * n, 3), dtype=torch.float32, device=dev) if world > 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)              # all timed work (kernel, events, NCCL) goes on this stream
+    torch.cuda.set_stream(stream)
 
     def step(k_ev=None):
         if k_ev is not None:

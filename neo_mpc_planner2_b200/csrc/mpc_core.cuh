@@ -589,21 +589,22 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
     float gn[S][3], pgn[S][3];
     fw.backward(P, I, xt, lg, gn);
     const float pgmax_n = Grp<G>::max(projected_gradient<S>(P, xt, gn, pgn));
+    // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
+    // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
+    // (The reductions are warp collectives: every lane executes them, whatever its group decides below.)
+    float sy = 0.0f, yy = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      NEOMPC_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pg[j][q];
+        sy += sv * yv; yy += yv * yv;
+        d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
+      }
+    }
+    sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy);
     if (active) {
       if (accepted) {
-        // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
-        // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
-        float sy = 0.0f, yy = 0.0f;
-        NEOMPC_UNROLL
-        for (int j = 0; j < S; ++j) {
-          NEOMPC_UNROLL
-          for (int q = 0; q < 3; ++q) {
-            const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pg[j][q];
-            sy += sv * yv; yy += yv * yv;
-            d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
-          }
-        }
-        sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy);
         if (sy > 1e-10f * yy && yy > 0.0f) {
           float* sp = hist + (size_t)(head * PAIR) * stride;
           NEOMPC_UNROLL
@@ -665,7 +666,9 @@ NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const n
     I.bx = (int)bxd; I.by = (int)byd;
     I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
   }
-  const bool fp_hit = valid && footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  // (every lane of the warp runs the collective inside footprint_lethal, also for groups without an instance)
+  const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  const bool fp_hit = valid && fp_any;
   {
     const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
     I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);        // srv.py:266,268 ; :262-263
@@ -804,7 +807,8 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
     I.bx = (int)bxd; I.by = (int)byd;
     I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
   }
-  const bool fp_hit = valid && footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+  const bool fp_hit = valid && fp_any;
   const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
   I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);
   float u[S][3], g[S][3];

@@ -131,7 +131,10 @@ class BatchSolver:
                                                  ctypes.c_void_p(plan_ptr) if plan_ptr else None), "neompc_solve_batch")
 
     def solve_device(self, d_reqs, n, d_out, d_twist=None, d_plan=None, stream=None):
-        """Device pointers (ints) in and out, asynchronous on `stream` (a cudaStream_t as int; None = handle stream)."""
+        """Device pointers (ints) in and out, asynchronous on `stream`: a cudaStream_t as int (0 = the legacy default
+        stream, which CUDA names by the handle 0x1), or None for the handle's own stream."""
+        if stream == 0:
+            stream = 1          # cudaStreamLegacy
         self._check(self._lib.neompc_solve_batch_device(
             self._h, ctypes.c_void_p(d_reqs), int(n), ctypes.c_void_p(d_out),
             ctypes.c_void_p(d_twist) if d_twist else None, ctypes.c_void_p(d_plan) if d_plan else None,
