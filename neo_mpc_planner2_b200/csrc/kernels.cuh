@@ -13,8 +13,8 @@ constexpr int kMaxStepsPerLane = 6;
 
 struct LaunchArgs {
   SolverConst P;
-  const float* lut_cost;       // device [257]
-  const uint8_t* lut_flag;     // device [257]
+  const float* lut_cost;       // device [kTableSize]
+  const uint8_t* lut_flag;     // device [kTableSize]
   const neompc_request* reqs;  // device [n]
   unsigned n;
   neompc_response* out;        // device [n]
@@ -29,12 +29,12 @@ struct LaunchArgs {
 
 // cost tables staged once per block in shared memory
 struct SmemTables {
-  float cost[257];
-  uint8_t flag[260];
+  float cost[kTableSize];
+  uint8_t flag[kTableSize + 2];
 };
 
 __device__ __forceinline__ void load_tables(SmemTables& st, const float* lut_cost, const uint8_t* lut_flag) {
-  for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kTableSize; i += blockDim.x) {
     st.cost[i] = __ldg(lut_cost + i);
     st.flag[i] = __ldg(lut_flag + i);
   }
@@ -55,8 +55,11 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
   return rq;
 }
 
+// resident blocks per SM the register allocator is asked to allow (65536 regs / (128 threads * blocks))
+constexpr int min_blocks_for(int S) { return S == 2 ? 5 : S == 1 || S == 3 ? 4 : S == 4 ? 3 : 2; }
+
 template <int G, int S>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
 solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
              const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
              neompc_response* __restrict__ out, float* __restrict__ twist, float* __restrict__ plan) {

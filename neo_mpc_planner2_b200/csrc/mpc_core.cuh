@@ -42,6 +42,9 @@ namespace neompc {
 constexpr int kMaxMemory = 8;          // compile-time cap of L-BFGS pairs
 constexpr int kMaxBacktracks = 12;     // arc-search halvings per iteration
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kCellOob = 256;          // cost-table index of "outside the map" (cost 1.0, lethal)
+constexpr int kCellFree = 257;         // cost-table index of "no costmap loaded" (cost 0)
+constexpr int kTableSize = 258;
 
 // ---------------------------------------------------------------------------------------------------------
 // Per-handle constants, precomputed on the host (runtime.cu: build_const) and passed by value to the kernels.
@@ -51,6 +54,7 @@ struct SolverConst {
   int m;               // L-BFGS memory
   int max_iter;
   int disc_only;       // 1: disc lies inside the box -> projection is a radial scaling (README parameters)
+  int fast_trig;       // 1: max|omega| * prediction_horizon <= pi -> MUFU sin/cos inside the rollout
   float dt;            // prediction_horizon / N                      (srv.py:137)
   float a_trans;       // w_trans / N                                 (srv.py:252)
   float b_orient;      // w_orient / N
@@ -82,8 +86,8 @@ struct SolverConst {
 // tables derived from (encoding, w_costmap, N): lut_cost[b] = (c==1 ? 1000 : w_costmap) * c^2 / N  (srv.py:247,257-260)
 // lut_flag[b]: bit0 c == 1.0 (lethal), bit1 c >= 0.99 (srv.py:338)
 struct CostTables {
-  const float* cost;      // [257]  entry 256 = out-of-bounds (c = 1.0)
-  const uint8_t* flag;    // [257]
+  const float* cost;      // [kTableSize]  entry 256 = out-of-bounds (c = 1.0), entry 257 = no costmap (0)
+  const uint8_t* flag;    // [kTableSize]
 };
 
 constexpr int kStateExtra = 12;   // floats after the 3N guess in a state row
@@ -171,24 +175,39 @@ NEOMPC_HD void sincos_f(float a, float* s, float* c) {
 #endif
 }
 
+// sin/cos of the accumulated heading inside the rollout.  |a| <= max|omega| * prediction_horizon; when that bound is
+// <= pi (SolverConst::fast_trig) the MUFU path is used: absolute error <= 2^-21.4 on [-pi, pi] (CUDA C Programming
+// Guide, intrinsic table), which moves a rollout position by < 1e-8 m.
+NEOMPC_HD void sincos_heading(bool fast, float a, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  if (fast) __sincosf(a, s, c); else sincosf(a, s, c);
+#else
+  (void)fast;
+  *s = sinf(a);
+  *c = cosf(a);
+#endif
+}
+
+NEOMPC_HD float rsqrt_f(float v) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(v);
+#else
+  return 1.0f / sqrtf(v);
+#endif
+}
+
 NEOMPC_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Euclidean projection of one control step onto  [lo,hi]^3 ∩ { vx^2 + vy^2 <= R^2 }
 // (bounds srv.py:127-133; disc constraint srv.py:157-158).  omega only sees its interval.
 // ---------------------------------------------------------------------------------------------------------
-NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& om) {
-  om = clampf(om, P.lo[2], P.hi[2]);
+// General case (the disc is not contained in the box); kept out of line: the README parameters never take it.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+inline void project_general(const SolverConst& P, float& vx, float& vy) {
   const float R2 = P.R * P.R;
-  if (P.disc_only) {
-    const float n2 = vx * vx + vy * vy;
-    if (n2 > R2) {
-      const float sc = P.R / sqrtf(n2);
-      vx *= sc;
-      vy *= sc;
-    }
-    return;
-  }
   const float bx = clampf(vx, P.lo[0], P.hi[0]);
   const float by = clampf(vy, P.lo[1], P.hi[1]);
   if (bx * bx + by * by <= R2) {      // box projection already inside the disc
@@ -209,14 +228,12 @@ NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& o
   // Otherwise the projection is a vertex of the feasible region: a box-edge line meeting the circle.
   float best = 3.4e38f, ox = bx, oy = by;
   bool found = false;
-  NEOMPC_UNROLL
   for (int e = 0; e < 4; ++e) {
     const bool xedge = e < 2;                          // x fixed at a bound, y on the circle
     const float fixed = xedge ? (e == 0 ? P.lo[0] : P.hi[0]) : (e == 2 ? P.lo[1] : P.hi[1]);
     const float rem = R2 - fixed * fixed;
     if (rem < 0.0f) continue;
     const float root = sqrtf(rem);
-    NEOMPC_UNROLL
     for (int sgn = 0; sgn < 2; ++sgn) {
       const float other = sgn ? root : -root;
       const float lo_o = xedge ? P.lo[1] : P.lo[0];
@@ -236,6 +253,18 @@ NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& o
   vx = ox; vy = oy;
 }
 
+NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& om) {
+  om = clampf(om, P.lo[2], P.hi[2]);
+  if (P.disc_only) {                                   // radial scaling, branch-free
+    const float n2 = vx * vx + vy * vy;
+    const float sc = fminf(1.0f, P.R * rsqrt_f(fmaxf(n2, 1e-30f)));
+    vx *= sc;
+    vy *= sc;
+  } else {
+    project_general(P, vx, vy);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Per-instance constants (hoisted out of objective(): srv.py:207-221)
 // ---------------------------------------------------------------------------------------------------------
@@ -252,27 +281,29 @@ struct Instance {
 
 template <int G, int S>
 struct Forward {
-  float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S];
+  float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
 
-  // cell lookup for a base-frame offset (x, y) rotated by (cr, sr) from the current position
+  // Table index of the cell under a base-frame offset (x, y) rotated by (cr, sr) from the current position:
+  // 0..255 = the cell byte, kCellOob = outside the map, kCellFree = no costmap loaded.  Branch-free.
   static NEOMPC_HD int cell_of(const SolverConst& P, const Instance& I, float cr, float sr, float x, float y) {
-    if (P.cells == nullptr) return 0 - 1;                      // free space
+    if (P.cells == nullptr) return kCellFree;                  // uniform
     const float gx = I.fx + (cr * x - sr * y) * P.inv_res;
     const float gy = I.fy + (sr * x + cr * y) * P.inv_res;
     const int mx = I.bx + (int)floorf(gx);
     const int my = I.by + (int)floorf(gy);
-    if (mx < 0 || my < 0 || mx >= P.W || my >= P.H) return 256;  // out of bounds
+    const bool inb = (unsigned)mx < (unsigned)P.W && (unsigned)my < (unsigned)P.H;
+    const size_t idx = inb ? (size_t)my * P.W + mx : 0;
 #if defined(__CUDA_ARCH__)
-    return (int)__ldg(P.cells + (size_t)my * P.W + mx);
+    const int cell = (int)__ldg(P.cells + idx);
 #else
-    return (int)P.cells[(size_t)my * P.W + mx];
+    const int cell = (int)P.cells[idx];
 #endif
+    return inb ? cell : kCellOob;
   }
 
-  // Rolls the omni-drive model over the horizon (srv.py:230-236) and returns this lane's share of J.
-  // u[j][0..2] = (vx, vy, omega) of step lg*S + j.  smooth: use sqrt(r^2+eps^2) for the control term.
-  NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3],
-                      int lg, bool with_costmap) {
+  // Rolls the omni-drive model over the horizon (srv.py:230-232): z, cos/sin, per-step displacement, position.
+  // u[j][0..2] = (vx, vy, omega) of step lg*S + j.
+  NEOMPC_HD void rollout(const SolverConst& P, const float (*u)[3], int lg) {
     const float dt = P.dt;
     // z_i = dt * sum_{k<=i} omega_k                                               (srv.py:230)
     float acc = 0.0f;
@@ -283,7 +314,7 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       z[j] += zoff;
-      sincos_f(z[j], &s[j], &c[j]);
+      sincos_heading(P.fast_trig != 0, z[j], &s[j], &c[j]);
       dx[j] = (u[j][0] * c[j] - u[j][1] * s[j]) * dt;                              // srv.py:231
       dy[j] = (u[j][0] * s[j] + u[j][1] * c[j]) * dt;                              // srv.py:232
       ax += dx[j]; x[j] = ax;
@@ -291,28 +322,38 @@ struct Forward {
     }
     const float xoff = Grp<G>::excl_prefix(ax, lg);
     const float yoff = Grp<G>::excl_prefix(ay, lg);
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { x[j] += xoff; y[j] += yoff; }
+  }
+
+  // This lane's share of J (srv.py:246-268) for the rollout held in the struct.  The control term uses
+  // sqrt(r^2 + eps^2); its reciprocal is kept for backward().
+  NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg) {
+    int cell[S];
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j)                                                     // srv.py:246-247 via :234-236
+      cell[j] = cell_of(P, I, I.cq, I.sq, x[j], y[j]);                              // (loads issued together)
     float J = 0.0f;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      x[j] += xoff;
-      y[j] += yoff;
       const int i = lg * S + j;
-      if (i < P.N) {
-        const float ex = I.cx - x[j], ey = I.cy - y[j], eo = I.tyaw - z[j];
-        J += P.a_trans * (ex * ex + ey * ey) + P.b_orient * (eo * eo);              // srv.py:250-252
-        const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
-        J += P.w_ctrl * sqrtf(rx * rx + ry * ry + rz * rz + P.eps2);                // srv.py:253-254 (smoothed)
-        if (with_costmap) {
-          const int cell = cell_of(P, I, I.cq, I.sq, x[j], y[j]);                   // srv.py:246-247 via :234-236
-          if (cell >= 0) J += T.cost[cell];                                         // srv.py:257-260
-        }
-        if (i == P.N - 1) {
-          const float ef = I.fyaw - z[j];
-          J += P.bt_term * (ef * ef);                                               // srv.py:267-268
-        }
-      }
+      const float ex = I.cx - x[j], ey = I.cy - y[j], eo = I.tyaw - z[j];
+      float st = P.a_trans * (ex * ex + ey * ey) + P.b_orient * (eo * eo);          // srv.py:250-252
+      const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+      const float r2 = fmaxf(rx * rx + ry * ry + rz * rz + P.eps2, 1e-24f);
+      rinv[j] = rsqrt_f(r2);
+      st += P.w_ctrl * (r2 * rinv[j]);                                              // srv.py:253-254 (smoothed)
+      st += T.cost[cell[j]];                                                        // srv.py:257-260
+      const float ef = I.fyaw - z[j];
+      st += (i == P.N - 1) ? P.bt_term * (ef * ef) : 0.0f;                          // srv.py:267-268
+      J += (i < P.N) ? st : 0.0f;
     }
     return J;
+  }
+
+  NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg) {
+    rollout(P, u, lg);
+    return cost(P, T, I, u, lg);
   }
 
   // Adjoint of run(): gradient of the smooth part of J w.r.t. this lane's controls.
@@ -329,7 +370,7 @@ struct Forward {
       gx[j] = on ? -2.0f * P.a_trans * (I.cx - x[j]) : 0.0f;
       gy[j] = on ? -2.0f * P.a_trans * (I.cy - y[j]) : 0.0f;
       gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
-      if (i == P.N - 1) gz[j] += -2.0f * P.bt_term * (I.fyaw - z[j]);
+      gz[j] += (i == P.N - 1) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
       sx += gx[j]; gx[j] = sx;                  // local inclusive suffix sums
       sy += gy[j]; gy[j] = sy;
     }
@@ -347,16 +388,12 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
-      if (i < P.N) {
-        const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
-        const float k = P.w_ctrl / sqrtf(rx * rx + ry * ry + rz * rz + P.eps2);
-        const float kk = (rx * rx + ry * ry + rz * rz + P.eps2) > 0.0f ? k : 0.0f;
-        g[j][0] = dt * (c[j] * gx[j] + s[j] * gy[j]) + kk * rx;
-        g[j][1] = dt * (-s[j] * gx[j] + c[j] * gy[j]) + kk * ry;
-        g[j][2] = dt * (gz[j] + sgoff) + kk * rz;
-      } else {
-        g[j][0] = g[j][1] = g[j][2] = 0.0f;
-      }
+      const bool on = i < P.N;
+      const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+      const float kk = P.w_ctrl * rinv[j];
+      g[j][0] = on ? dt * (c[j] * gx[j] + s[j] * gy[j]) + kk * rx : 0.0f;
+      g[j][1] = on ? dt * (-s[j] * gx[j] + c[j] * gy[j]) + kk * ry : 0.0f;
+      g[j][2] = on ? dt * (gz[j] + sgoff) + kk * rz : 0.0f;
     }
   }
 };
@@ -367,11 +404,10 @@ NEOMPC_HD float unsmooth_correction(const SolverConst& P, const Instance& I, con
   float d = 0.0f;
   NEOMPC_UNROLL
   for (int j = 0; j < S; ++j) {
-    if (lg * S + j < P.N) {
-      const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
-      const float r2 = rx * rx + ry * ry + rz * rz;
-      d += P.w_ctrl * (sqrtf(r2) - sqrtf(r2 + P.eps2));
-    }
+    const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+    const float r2 = rx * rx + ry * ry + rz * rz;
+    const float v = P.w_ctrl * (sqrtf(r2) - sqrtf(r2 + P.eps2));
+    d += (lg * S + j < P.N) ? v : 0.0f;
   }
   return Grp<G>::sum(d);
 }
@@ -411,7 +447,7 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
       const int minor = den > 0 ? (den / 2 + k * numadd) / den : 0;
       const int cxp = xmaj ? mx0 + k * sxs : mx0 + minor * sxs;
       const int cyp = xmaj ? my0 + minor * sys : my0 + k * sys;
-      int cell = 256;
+      int cell = kCellOob;
       if (cxp >= 0 && cyp >= 0 && cxp < P.W && cyp < P.H) {
 #if defined(__CUDA_ARCH__)
         cell = (int)__ldg(P.cells + (size_t)cyp * P.W + cxp);
@@ -429,24 +465,16 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
 // ---------------------------------------------------------------------------------------------------------
 // History storage for L-BFGS: element e of this lane lives at hist[e * stride] (stride = threads per
 // block in shared memory -> conflict-free; 1 in the host build).
-// Per pair p (0..m-1): [3S floats s][3S floats y][1 float rho]
+// Per pair p (0..m-1): [3S floats s][3S floats y][rho][alpha scratch of the two-loop recursion]
 // ---------------------------------------------------------------------------------------------------------
 template <int S>
-NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 1); }
+NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2); }
 
 struct SolveOut {
   float cost;
   unsigned iters, evals, status;
 };
 
-// ---------------------------------------------------------------------------------------------------------
-// Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc).
-//   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion; pg = x - Proj(x - g) is the
-//   projected gradient), Armijo backtracking along the projection arc on the TRUE piecewise-constant-
-//   including objective; falls back to a projected-gradient step when the quasi-Newton arc fails.
-// u holds the start point on entry (any point; it is projected) and the solution on exit.
-// `valid` = this group owns an instance; invalid groups only take part in the warp-wide votes/shuffles.
-// ---------------------------------------------------------------------------------------------------------
 template <int S>
 NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
   float pgmax = 0.0f;
@@ -460,67 +488,79 @@ NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], co
   return pgmax;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc).
+//   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion; pg = x - Proj(x - g) is the
+//   projected gradient; the secant pairs are those of the map pg, so an active disc constraint contributes
+//   its curvature), Armijo backtracking along the projection arc on the true objective incl. the piecewise-
+//   constant costmap term; falls back to a projected-gradient step when the quasi-Newton arc fails.
+// u holds the start point on entry (any point; it is projected) and the solution on exit.
+// `valid` = this group owns an instance; invalid groups only take part in the warp-wide votes/shuffles.
+// The first pass through the loop body only evaluates the start point (one copy of the rollout code).
+// ---------------------------------------------------------------------------------------------------------
 template <int G, int S>
 NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Instance& I, float (*u)[3],
                            float* hist, int stride, int lg, bool valid, SolveOut& out) {
-  constexpr int PAIR = 6 * S + 1;
+  constexpr int PAIR = 6 * S + 2;
   const int m = P.m;
   Forward<G, S> fw;
-  float g[S][3], d[S][3], xt[S][3], pg[S][3];
+  float g[S][3], d[S][3], xt[S][3], pg[S][3], r[S][3];
 
   NEOMPC_UNROLL
   for (int j = 0; j < S; ++j) {
     if (lg * S + j >= P.N) { u[j][0] = u[j][1] = u[j][2] = 0.0f; }
     project_step(P, u[j][0], u[j][1], u[j][2]);
+    NEOMPC_UNROLL
+    for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; d[j][q] = 0.0f; pg[j][q] = 0.0f; }
   }
-  for (int e = 0; e < m * PAIR; ++e) hist[e * stride] = 0.0f;
+  for (int e = 0; e < m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
 
-  float f = Grp<G>::sum(fw.run(P, T, I, u, lg, true));
-  fw.backward(P, I, u, lg, g);
-  float pgmax = Grp<G>::max(projected_gradient<S>(P, u, g, pg));
-  unsigned iters = 0, evals = 1, status = NEOMPC_STATUS_MAXITER;
+  float f = 0.0f, pgmax = 0.0f;
+  unsigned iters = 0, evals = 0, status = NEOMPC_STATUS_MAXITER;
   int hist_len = 0, head = 0;
   float gamma = 1.0f;
   bool active = valid;
   bool force_pg = true;          // no curvature information yet
+  bool first = true;             // warp-uniform
   int small_steps = 0;
 
   while (true) {
-    // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
-    if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
-    if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
-    if (!Grp<G>::warp_any(active)) break;
+    bool qn_dir = false;
+    float alpha = 0.0f;
+    if (!first) {
+      // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
+      if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+      if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
+      if (!Grp<G>::warp_any(active)) break;
 
-    // ---- direction: two-loop recursion on the projected gradient
-    const bool use_qn = !force_pg && hist_len > 0;
-    float r[S][3];
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
-    float alpha_k[kMaxMemory];
-    NEOMPC_UNROLL
-    for (int k = 0; k < kMaxMemory; ++k) {
-      alpha_k[k] = 0.0f;
-      if (k < m) {
+      // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
+      const bool use_qn = !force_pg && hist_len > 0;
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int k = 0; k < m; ++k) {
         const bool on = use_qn && k < hist_len;
         int p = head - 1 - k; if (p < 0) p += m;
-        const float* sp = hist + (size_t)(p * PAIR) * stride;
+        float* sp = hist + (size_t)(p * PAIR) * stride;
         const float* yp = sp + (size_t)(3 * S) * stride;
         float dot = 0.0f;
         NEOMPC_UNROLL
         for (int e = 0; e < 3 * S; ++e) dot += sp[(size_t)e * stride] * r[e / 3][e % 3];
         dot = Grp<G>::sum(dot);
         const float a = on ? sp[(size_t)(6 * S) * stride] * dot : 0.0f;
-        alpha_k[k] = a;
+        sp[(size_t)(6 * S + 1) * stride] = a;
         NEOMPC_UNROLL
         for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
       }
-    }
-    const float h0 = use_qn ? gamma : 1.0f;
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
-    NEOMPC_UNROLL
-    for (int k = kMaxMemory - 1; k >= 0; --k) {
-      if (k < m) {
+      const float h0 = use_qn ? gamma : 1.0f;
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int k = m - 1; k >= 0; --k) {
         const bool on = use_qn && k < hist_len;
         int p = head - 1 - k; if (p < 0) p += m;
         const float* sp = hist + (size_t)(p * PAIR) * stride;
@@ -529,31 +569,31 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         NEOMPC_UNROLL
         for (int e = 0; e < 3 * S; ++e) dot += yp[(size_t)e * stride] * r[e / 3][e % 3];
         dot = Grp<G>::sum(dot);
-        const float b = on ? alpha_k[k] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
+        const float b = on ? sp[(size_t)(6 * S + 1) * stride] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
         NEOMPC_UNROLL
         for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] += b * sp[(size_t)e * stride];
       }
-    }
-    // d = -r; it must be a descent direction for the projected gradient, else restart from -pg
-    float gd = 0.0f, pgn2 = 0.0f;
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) {
+      // d = -r; it must be a descent direction for the projected gradient, else restart from -pg
+      float gd = 0.0f, pgn2 = 0.0f;
       NEOMPC_UNROLL
-      for (int q = 0; q < 3; ++q) {
-        d[j][q] = -r[j][q];
-        gd += pg[j][q] * d[j][q];
-        pgn2 += pg[j][q] * pg[j][q];
+      for (int j = 0; j < S; ++j) {
+        NEOMPC_UNROLL
+        for (int q = 0; q < 3; ++q) {
+          d[j][q] = -r[j][q];
+          gd += pg[j][q] * d[j][q];
+          pgn2 += pg[j][q] * pg[j][q];
+        }
       }
-    }
-    gd = Grp<G>::sum(gd);
-    pgn2 = Grp<G>::sum(pgn2);
-    const bool qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
-    float alpha = 1.0f;
-    if (!qn_dir) {
-      NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
-      // first trial moves the largest component by about the velocity range
-      alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+      gd = Grp<G>::sum(gd);
+      pgn2 = Grp<G>::sum(pgn2);
+      qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
+      alpha = 1.0f;
+      if (!qn_dir) {
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
+        // first trial moves the largest component by about the velocity range
+        alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+      }
     }
 
     // ---- Armijo backtracking along the projection arc (all groups of the warp in lock step)
@@ -570,20 +610,17 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
       }
       gs = Grp<G>::sum(gs);
-      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg, true));
+      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg));
       if (!ls_done) {
         ++evals;
         ft = ftrial;
-        if (ftrial <= f + 1e-4f * gs && gs < 0.0f) { ls_done = true; accepted = true; }
+        if (first || (ftrial <= f + 1e-4f * gs && gs < 0.0f)) { ls_done = true; accepted = true; }
       }
       if (!Grp<G>::warp_any(!ls_done)) break;
       if (!ls_done) alpha *= 0.5f;
     }
     NEOMPC_TRACE("it %u f %.7f pgmax %.3e qn %d alpha %.4g acc %d ft %.7f evals %u hist %d\n", iters, f, pgmax,
                  (int)qn_dir, alpha, (int)accepted, ft, evals, hist_len);
-    for (int j = 0; j < S; ++j)
-      NEOMPC_TRACE("      u %+.4f %+.4f %+.4f   pg %+.2e %+.2e %+.2e  g %+.2e %+.2e %+.2e\n", u[j][0], u[j][1], u[j][2],
-                   pg[j][0], pg[j][1], pg[j][2], g[j][0], g[j][1], g[j][2]);
 
     // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
     float gn[S][3], pgn[S][3];
@@ -605,7 +642,7 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
     sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy);
     if (active) {
       if (accepted) {
-        if (sy > 1e-10f * yy && yy > 0.0f) {
+        if (!first && sy > 1e-10f * yy && yy > 0.0f) {
           float* sp = hist + (size_t)(head * PAIR) * stride;
           NEOMPC_UNROLL
           for (int e = 0; e < 3 * S; ++e) {
@@ -626,10 +663,12 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         }
         f = ft;
         pgmax = pgmax_n;
-        ++iters;
-        // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
-        if (df <= P.tol_f * fmaxf(1.0f, fabsf(f))) ++small_steps; else small_steps = 0;
-        if (small_steps >= 2) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+        if (!first) {
+          ++iters;
+          // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
+          if (df <= P.tol_f * fmaxf(1.0f, fabsf(f))) ++small_steps; else small_steps = 0;
+          if (small_steps >= 2) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+        }
       } else if (qn_dir) {
         hist_len = 0; head = 0; force_pg = true;    // quasi-Newton arc failed: restart with projected gradient
         ++iters;
@@ -638,6 +677,7 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         status = NEOMPC_STATUS_LINESEARCH;
       }
     }
+    first = false;
   }
   out.cost = f;
   out.iters = iters;
@@ -719,14 +759,12 @@ NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const n
   }
   // ---- collision_check: re-roll with the TRUE yaw (srv.py:312-347)
   Forward<G, S> fw;
-  (void)fw.run(P, T, I, u, lg, false);
+  fw.rollout(P, u, lg);
   int hit = 0;
   NEOMPC_UNROLL
   for (int j = 0; j < S; ++j) {
-    if (lg * S + j < P.N) {
-      const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
-      if (cell >= 0) hit |= (T.flag[cell] >> 1) & 1;                                  // col >= 0.99, srv.py:338
-    }
+    const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
+    hit |= (lg * S + j < P.N) ? (T.flag[cell] >> 1) & 1 : 0;                          // col >= 0.99, srv.py:338
   }
   hit = Grp<G>::imax(hit);
   bool collision = latched || hit != 0;
@@ -821,7 +859,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
     u[j][2] = ld ? uin[3 * i + 2] : 0.0f;
   }
   Forward<G, S> fw;
-  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg, true));
+  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg));
   const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
   fw.backward(P, I, u, lg, g);
   if (!valid) return;

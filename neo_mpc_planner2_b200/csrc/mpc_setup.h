@@ -12,8 +12,8 @@
 namespace neompc {
 
 struct HostTables {
-  std::vector<float> cost;     // 257
-  std::vector<uint8_t> flag;   // 257
+  std::vector<float> cost;     // kTableSize
+  std::vector<uint8_t> flag;   // kTableSize
 };
 
 inline double cell_cost(int encoding, int byte) {
@@ -24,8 +24,8 @@ inline double cell_cost(int encoding, int byte) {
 
 // lut_cost[b] = (c == 1.0 ? 1000 : w_costmap) * c^2 / N     (srv.py:247, 257-260)
 inline void build_tables(const neompc_params& p, int encoding, HostTables& t) {
-  t.cost.assign(257, 0.0f);
-  t.flag.assign(257, 0);
+  t.cost.assign(kTableSize, 0.0f);          // entry kCellFree (no costmap) stays 0
+  t.flag.assign(kTableSize, 0);
   for (int b = 0; b <= 256; ++b) {
     const double c = b == 256 ? 1.0 : cell_cost(encoding, b);
     const double cc = c * c;
@@ -83,12 +83,13 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.bt_term = p.w_orient * p.w_terminal;
   c.wt_term = p.w_trans * p.w_terminal;
   c.w_fp = p.w_footprint;
-  const float eps = p.control_smoothing > 0.0f ? p.control_smoothing : 1e-2f;
+  const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f) : 1e-2f;
   c.eps2 = eps * eps;
   c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;
   c.hi[0] = p.max_vel_x; c.hi[1] = p.max_vel_y; c.hi[2] = p.max_vel_theta;
   c.R = p.max_vel_trans;
   c.disc_only = (p.max_vel_trans <= fminf(fminf(-p.min_vel_x, p.max_vel_x), fminf(-p.min_vel_y, p.max_vel_y))) ? 1 : 0;
+  c.fast_trig = (fmaxf(fabsf(p.min_vel_theta), fabsf(p.max_vel_theta)) * p.prediction_horizon <= 3.14159265f) ? 1 : 0;
   c.acc[0] = p.acc_x_limit; c.acc[1] = p.acc_y_limit; c.acc[2] = p.acc_theta_limit;
   c.lp_gain = p.low_pass_gain;
   c.tol_pg = kPgScale * p.opt_tolerance;

@@ -59,8 +59,8 @@ int cuda_fail(neompc_handle* h, cudaError_t e, const char* what) {
 
 int upload_tables(neompc_handle* h) {
   build_tables(h->params, h->encoding, h->tab);
-  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_cost, h->tab.cost.data(), 257 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_flag, h->tab.flag.data(), 257, cudaMemcpyHostToDevice, h->stream));
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_cost, h->tab.cost.data(), kTableSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_flag, h->tab.flag.data(), kTableSize, cudaMemcpyHostToDevice, h->stream));
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   return NEOMPC_OK;
 }
@@ -221,8 +221,8 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CREATE_CUDA(cudaMalloc(&h->d_lut_cost, 257 * sizeof(float)));
-  CREATE_CUDA(cudaMalloc(&h->d_lut_flag, 260));
+  CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&h->d_lut_flag, kTableSize + 6));
 #undef CREATE_CUDA
   build_const(h->params, h->c);
   rebuild_const(h);
