@@ -587,6 +587,26 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
       gd = Grp<G>::sum(gd);
       pgn2 = Grp<G>::sum(pgn2);
       qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
+      // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
+      // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
+      // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
+      if (P.disc_only) {
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) {
+          const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
+          const float gr = g[j][0] * u[j][0] + g[j][1] * u[j][1];
+          const bool bind = n2 >= P.R * P.R * (1.0f - 2e-6f) && gr < 0.0f;
+          const float dr = (d[j][0] * u[j][0] + d[j][1] * u[j][1]) / fmaxf(n2, 1e-30f);
+          d[j][0] -= bind ? dr * u[j][0] : 0.0f;
+          d[j][1] -= bind ? dr * u[j][1] : 0.0f;
+        }
+      }
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        const bool at_lo = u[j][2] <= P.lo[2] && g[j][2] > 0.0f;
+        const bool at_hi = u[j][2] >= P.hi[2] && g[j][2] < 0.0f;
+        d[j][2] = (at_lo || at_hi) ? 0.0f : d[j][2];
+      }
       alpha = 1.0f;
       if (!qn_dir) {
         NEOMPC_UNROLL
@@ -617,10 +637,20 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         if (first || (ftrial <= f + 1e-4f * gs && gs < 0.0f)) { ls_done = true; accepted = true; }
       }
       if (!Grp<G>::warp_any(!ls_done)) break;
-      if (!ls_done) alpha *= 0.5f;
+      if (!ls_done) {
+        // not a descent arc at all: give up on this direction at once (the fallback below takes over)
+        if (gs >= 0.0f && bt == 0 && qn_dir) { ls_done = true; }
+        // safeguarded quadratic interpolation of the step length
+        const float denom = 2.0f * (ftrial - f - gs);
+        const float aq = denom > 0.0f ? -gs / denom : 0.5f;
+        alpha *= fminf(0.5f, fmaxf(0.1f, aq));
+      }
     }
     NEOMPC_TRACE("it %u f %.7f pgmax %.3e qn %d alpha %.4g acc %d ft %.7f evals %u hist %d\n", iters, f, pgmax,
                  (int)qn_dir, alpha, (int)accepted, ft, evals, hist_len);
+    for (int j = 0; j < S; ++j)
+      NEOMPC_TRACE("      u %+.4f %+.4f %+.4f   pg %+.2e %+.2e %+.2e  g %+.2e %+.2e %+.2e  d %+.2e %+.2e %+.2e\n", u[j][0],
+                   u[j][1], u[j][2], pg[j][0], pg[j][1], pg[j][2], g[j][0], g[j][1], g[j][2], d[j][0], d[j][1], d[j][2]);
 
     // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
     float gn[S][3], pgn[S][3];

@@ -104,8 +104,10 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
 inline void choose_tiling(int n_steps, int lanes_override, int* G, int* S) {
   int g = lanes_override;
   if (g <= 0) {
+    // measured on B200 (profiles/tiling_sweep_r1.txt): 3 steps per lane is fastest for N = 10 and 20, 2 for N = 3
+    const int target = n_steps <= 4 ? 2 : 3;
     g = 1;
-    while ((n_steps + g - 1) / g > 3 && g < 32) g <<= 1;       // default: at most 3 steps per lane
+    while ((n_steps + g - 1) / g > target && g < 32) g <<= 1;
   }
   while ((n_steps + g - 1) / g > 6 && g < 32) g <<= 1;         // S is instantiated up to 6
   *G = g;

@@ -1,0 +1,126 @@
+"""CPU-side checks of the solver core through its host emulation (tests/hostsim: the SAME mpc_core.cuh compiled by
+g++ with one lane per instance).  This is test tooling — the product has no CPU path — but it lets the algorithm
+(projection, analytic gradient, projected L-BFGS, optimizer() epilogue) be checked against the oracle on machines
+without a GPU.  The GPU tests repeat these checks through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.costmap import GridCostmap
+from oracle.mpc_oracle import REQUEST_FIELDS
+from neo_mpc_planner2_b200 import workloads
+from neo_mpc_planner2_b200.abi import REQUEST_DTYPE, README_SAMPLE
+from tests.hostsim import HostSim
+from tests.util import (setup_workload, footprint_lethal_flags, near_cell_edge, feasibility_violation,
+                        scipy_solutions)
+
+
+def _hs(wl, **knobs):
+    return HostSim(wl.params, wl.cells, wl.resolution, (wl.origin_x, wl.origin_y), footprint=wl.footprint, **knobs)
+
+
+@pytest.mark.parametrize("cfg,n_steps", [("c2", 3), ("c3", 10), ("c3", 20)])
+def test_objective_and_gradient(cfg, n_steps):
+    wl, p, cm = setup_workload(cfg, 512, n_steps)
+    rng = np.random.default_rng(1)
+    U = rng.uniform(-0.7, 0.7, (wl.batch, 3 * n_steps)).astype(np.float32)
+    J, G = _hs(wl).eval(wl.requests, U)
+    fpl = footprint_lethal_flags(wl, cm)
+    Jo = oracle.objective_batch(p, cm, wl.requests, U.astype(np.float64), fp_lethal=fpl)
+    err = np.abs(J - Jo) / np.maximum(1.0, np.abs(Jo))
+    edge = near_cell_edge(p, cm, wl.requests, U.astype(np.float64))
+    assert err[~edge].max() <= 2e-5
+    Go = oracle.gradient_batch(p, wl.requests, U.astype(np.float64), eps_control=1e-2)
+    assert np.abs(G - Go).max() <= 2e-5
+
+
+def test_projection_properties():
+    """Projection onto box ∩ disc: feasible, idempotent, and never farther than any feasible grid point."""
+    rng = np.random.default_rng(2)
+    cases = [dict(README_SAMPLE),
+             dict(README_SAMPLE, max_vel_x=0.6, min_vel_x=-0.1, max_vel_y=0.3, min_vel_y=-0.3, max_vel_trans=0.5),
+             dict(README_SAMPLE, max_vel_x=0.2, min_vel_x=-0.2, max_vel_y=0.9, min_vel_y=-0.9, max_vel_trans=0.7),
+             dict(README_SAMPLE, max_vel_x=0.3, min_vel_x=-0.3, max_vel_y=0.3, min_vel_y=-0.3, max_vel_trans=0.9)]
+    for prm in cases:
+        hs = HostSim(prm)
+        V = rng.uniform(-1.5, 1.5, (4000, 3)).astype(np.float32)
+        Pv = hs.project(V)
+        lo = np.array([prm["min_vel_x"], prm["min_vel_y"], prm["min_vel_theta"]])
+        hi = np.array([prm["max_vel_x"], prm["max_vel_y"], prm["max_vel_theta"]])
+        assert (Pv >= lo - 1e-6).all() and (Pv <= hi + 1e-6).all()
+        assert (np.hypot(Pv[:, 0], Pv[:, 1]) <= prm["max_vel_trans"] + 1e-6).all()
+        assert np.abs(hs.project(Pv) - Pv).max() <= 1e-6
+        # optimality against a dense sample of the feasible set
+        gx, gy = np.meshgrid(np.linspace(lo[0], hi[0], 121), np.linspace(lo[1], hi[1], 121))
+        ok = gx ** 2 + gy ** 2 <= prm["max_vel_trans"] ** 2
+        F = np.stack([gx[ok], gy[ok]], 1)
+        for k in range(0, 4000, 97):
+            d_best = np.sqrt(((F - V[k, :2]) ** 2).sum(1)).min()
+            d_proj = np.hypot(*(Pv[k, :2] - V[k, :2]))
+            assert d_proj <= d_best + 1e-5
+
+
+@pytest.mark.parametrize("cfg,n_steps,count", [("c1", 3, 1), ("c2", 3, 48), ("c3", 10, 12)])
+def test_solver_reaches_scipy_cost(cfg, n_steps, count):
+    wl, p, cm = setup_workload(cfg, 64 if cfg != "c1" else None, n_steps)
+    out, plan = _hs(wl).solve(wl.requests)
+    assert feasibility_violation(wl.params, plan) <= 1e-6
+    fpl = footprint_lethal_flags(wl, cm)
+    Jg = oracle.objective_batch(p, cm, wl.requests, plan.astype(np.float64), fp_lethal=fpl)
+    idx = list(range(min(count, wl.batch)))
+    ref = scipy_solutions(wl, p, cm, idx)
+    dJ = np.array([Jg[i] - float(r.fun) for i, (r, _) in zip(idx, ref)])
+    assert dJ.max() <= 5 * p.opt_tolerance
+    assert (dJ > 1e-4).sum() <= max(1, len(dJ) // 16)
+    assert np.median(dJ) <= 0.0
+    assert (out["status"] != 1).all()
+
+
+def test_kat_solution_close_to_tight_scipy(golden):
+    """C1: the tightly converged reference optimum of the known-answer problem (golden 'slsqp_tight')."""
+    k = golden["kat"]
+    wl = workloads.config("c1")
+    out, plan = _hs(wl).solve(wl.requests)
+    p = oracle.MpcParams(**wl.params)
+    Jg = oracle.objective_batch(p, None, wl.requests, plan.astype(np.float64))[0]
+    assert Jg <= k["slsqp"]["fun"] + 1e-6            # better than the reference's ftol=1e-3 result
+    assert Jg <= k["slsqp_tight"]["fun"] + 2e-4      # and within 2e-4 of the tight optimum
+    assert np.abs(plan[0, :3] - np.array(k["slsqp_tight"]["x"][:3])).max() <= 2e-2
+
+
+def test_state_machine_sequences_on_host(golden):
+    """The optimizer() epilogue of the core against the oracle's state machine over the golden tick sequences."""
+    wl = workloads.config("c2", batch=64)
+    for seq in golden["tick_sequences"]:
+        if seq["grid"] is None:
+            cells = None
+        elif seq["name"].startswith("c2map"):
+            cells = wl.cells
+        elif seq["name"].startswith("wall"):
+            cells = np.zeros((200, 200), np.uint8); cells[:, 112:] = 99; cells[:, 116:] = 100
+        else:
+            cells = np.zeros((200, 200), np.uint8); cells[100:104, 106:110] = 100
+        params = seq["params"]
+        p = oracle.MpcParams(**params)
+        cm = GridCostmap(cells, 0.05, *seq["origin"]) if cells is not None else oracle.costmap.FreeSpaceCostmap()
+        osrv = oracle.OracleServer(p, cm, seq["footprint_robot"])
+        hs = HostSim(params, cells, 0.05, tuple(seq["origin"]), footprint=seq["footprint_robot"], state_rows=2)
+        for t in seq["ticks"]:
+            req = np.zeros(1, REQUEST_DTYPE)
+            for f in REQUEST_FIELDS:
+                req[f] = t["problem"][f]
+            req["pose_yaw"] = t["problem"]["pose_yaw_true"]
+            req["delta_t"] = min(t["problem"]["delta_t"], 3.0e38)
+            req["instance_id"] = 1
+            out, plan = hs.solve(req)
+            ok = int(out["status"][0]) != 1
+            o = osrv.tick(oracle.Problem.from_record(req[0]),
+                          solver=lambda x0, prob, fpw: (plan[0].astype(np.float64), ok))
+            got = (float(out["vx"][0]), float(out["vy"][0]), float(out["omega"][0]))
+            assert max(abs(a - b) for a, b in zip(got, o)) <= 1e-6, seq["name"]
+            assert bool(out["flags"][0] & 1) == osrv.collision
+            assert bool(out["flags"][0] & 2) == osrv.collision_footprint
+            n3 = 3 * p.control_steps
+            row = hs.state[1]
+            assert np.abs(row[:n3] - osrv.initial_guess).max() <= 1e-6
+            assert row[n3 + 3] == pytest.approx(osrv.waiting_time, abs=1e-5)
