@@ -56,7 +56,10 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 }
 
 // resident blocks per SM the register allocator is asked to allow (65536 regs / (128 threads * blocks))
-constexpr int min_blocks_for(int S) { return S == 2 ? 5 : S == 1 || S == 3 ? 4 : S == 4 ? 3 : 2; }
+#ifndef NEOMPC_MINBLOCKS_S3
+#define NEOMPC_MINBLOCKS_S3 4
+#endif
+constexpr int min_blocks_for(int S) { return S == 2 ? 5 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2; }
 
 template <int G, int S>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))

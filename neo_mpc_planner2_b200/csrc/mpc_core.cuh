@@ -203,27 +203,23 @@ NEOMPC_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo),
 // (bounds srv.py:127-133; disc constraint srv.py:157-158).  omega only sees its interval.
 // ---------------------------------------------------------------------------------------------------------
 // General case (the disc is not contained in the box); kept out of line: the README parameters never take it.
+// Takes and returns values so that callers' register arrays never have their address taken.
+struct Vec2 { float x, y; };
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #endif
-inline void project_general(const SolverConst& P, float& vx, float& vy) {
+inline Vec2 project_general(const SolverConst& P, float vx, float vy) {
   const float R2 = P.R * P.R;
   const float bx = clampf(vx, P.lo[0], P.hi[0]);
   const float by = clampf(vy, P.lo[1], P.hi[1]);
-  if (bx * bx + by * by <= R2) {      // box projection already inside the disc
-    vx = bx; vy = by;
-    return;
-  }
+  if (bx * bx + by * by <= R2) return Vec2{bx, by};   // box projection already inside the disc
   const float n2 = vx * vx + vy * vy;
   if (n2 > 0.0f) {
     const float sc = P.R / sqrtf(n2);
     const float rx = vx * sc, ry = vy * sc;
     const float t = 1e-6f;
-    if (rx >= P.lo[0] - t && rx <= P.hi[0] + t && ry >= P.lo[1] - t && ry <= P.hi[1] + t) {
-      vx = clampf(rx, P.lo[0], P.hi[0]);   // disc projection already inside the box
-      vy = clampf(ry, P.lo[1], P.hi[1]);
-      return;
-    }
+    if (rx >= P.lo[0] - t && rx <= P.hi[0] + t && ry >= P.lo[1] - t && ry <= P.hi[1] + t)
+      return Vec2{clampf(rx, P.lo[0], P.hi[0]), clampf(ry, P.lo[1], P.hi[1])};   // disc projection inside the box
   }
   // Otherwise the projection is a vertex of the feasible region: a box-edge line meeting the circle.
   float best = 3.4e38f, ox = bx, oy = by;
@@ -250,7 +246,7 @@ inline void project_general(const SolverConst& P, float& vx, float& vy) {
     ox = bx * P.R / n;
     oy = by * P.R / n;
   }
-  vx = ox; vy = oy;
+  return Vec2{ox, oy};
 }
 
 NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& om) {
@@ -261,7 +257,9 @@ NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& o
     vx *= sc;
     vy *= sc;
   } else {
-    project_general(P, vx, vy);
+    const Vec2 p = project_general(P, vx, vy);
+    vx = p.x;
+    vy = p.y;
   }
 }
 

@@ -74,7 +74,7 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   std::memset(&c, 0, sizeof(c));
   const int N = p.control_steps;
   c.N = N;
-  c.m = p.lbfgs_memory > 0 ? p.lbfgs_memory : 5;
+  c.m = p.lbfgs_memory > 0 ? p.lbfgs_memory : 3;   // iterations do not drop with more pairs (profiles/lbfgs_memory_r1.txt)
   c.max_iter = p.max_iterations > 0 ? p.max_iterations : 100;
   c.dt = p.prediction_horizon / (float)N;
   c.a_trans = p.w_trans / (float)N;
