@@ -25,6 +25,8 @@ struct LaunchArgs {
   float* J;                    // device [n]
   float* grad;                 // device [n*3N] or null
   cudaStream_t stream;
+  unsigned* queue_counter;     // device word for the persistent kernel's work queue; null = one instance per group
+  int sm_count;
 };
 
 // cost tables staged once per block in shared memory
@@ -81,6 +83,76 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
                        (valid && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
 }
 
+// Persistent variant: every lane group keeps pulling instances from a global counter until the batch is exhausted,
+// so a group that converges early does not idle while the slowest instance of its warp finishes (lock-step
+// efficiency of the one-instance-per-group kernel is ~0.6 at 8 instances per warp, profiles/lockstep_r1.txt).
+// The arithmetic of an instance does not depend on which group runs it or on its neighbours: results are
+// bit-identical to solve_kernel's.
+template <int G, int S>
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
+solve_queue_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
+                   const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
+                   neompc_response* __restrict__ out, float* __restrict__ twist, float* __restrict__ plan,
+                   unsigned* __restrict__ counter) {
+  extern __shared__ float hist_smem[];
+  __shared__ SmemTables st;
+  load_tables(st, lut_cost, lut_flag);
+  CostTables T{st.cost, st.flag};
+  constexpr int kGroupsPerBlock = kBlockThreads / G;
+  const int lg = threadIdx.x % G;
+  const unsigned lane = threadIdx.x & 31u;
+  float* hist = hist_smem + threadIdx.x;
+  const unsigned total_groups = gridDim.x * kGroupsPerBlock;
+
+  Solver<G, S> sv;
+  // a defined, inert state for groups that have not been given an instance yet
+  sv.prologue(P, T, load_request(reqs, 0, false), false, lg, hist, kBlockThreads);
+  unsigned inst = 0;
+  bool need = true, exhausted = false, first_round = true;
+
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kRefillAt = kGroupsPerWarp >= 4 ? kGroupsPerWarp / 2 : 1;   // refill once this many groups idle
+  while (true) {
+    const int idle = __popc(__ballot_sync(kFullMask, need && lg == 0));
+    const bool any_active = __any_sync(kFullMask, sv.active);
+    if (idle >= kRefillAt || (idle > 0 && !any_active)) {
+      // 1. finish the instances of the groups that just converged
+      const bool fin = need && sv.has_instance;
+      {
+        const neompc_request rq_done = load_request(reqs, inst, fin);
+        sv.epilogue(P, T, rq_done, fin, lg, fin ? out + inst : nullptr,
+                    (fin && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,
+                    (fin && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
+      }
+      // 2. next instance for every needy group: first round static, then one aggregated atomic per warp
+      unsigned nxt;
+      if (first_round) {
+        nxt = blockIdx.x * kGroupsPerBlock + threadIdx.x / G;
+      } else {
+        const unsigned want = __ballot_sync(kFullMask, need && lg == 0);
+        unsigned base = 0;
+        if (lane == 0 && want != 0) base = atomicAdd(counter, (unsigned)__popc(want));
+        base = __shfl_sync(kFullMask, base, 0);
+        nxt = total_groups + base + (unsigned)__popc(want & ((1u << lane) - 1u));
+        nxt = __shfl_sync(kFullMask, nxt, 0, G);          // lane 0 of each group holds the group's ticket
+      }
+      first_round = false;
+      const bool got = need && nxt < n;
+      const neompc_request rq = load_request(reqs, nxt, got);
+      const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+      if (need) {
+        sv.init(P, rq, fp_any, got, lg, hist, kBlockThreads);
+        inst = nxt;
+        exhausted = !got;
+      }
+      need = false;
+    }
+    if (!__any_sync(kFullMask, sv.active)) break;
+    sv.pass(P, T, hist, kBlockThreads, lg);
+    need = need || (!sv.active && !exhausted);
+  }
+}
+
 template <int G, int S>
 __global__ void __launch_bounds__(kBlockThreads)
 eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
@@ -102,12 +174,28 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
 template <int G, int S>
 cudaError_t launch_solve_gs(const LaunchArgs& a) {
   const size_t smem = (size_t)kBlockThreads * hist_floats_per_lane<S>(a.P.m) * sizeof(float);
+  constexpr int kInstPerBlock = kBlockThreads / G;
+  const unsigned blocks_needed = (a.n + kInstPerBlock - 1) / kInstPerBlock;
+  if (a.queue_counter != nullptr) {
+    // persistent launch: as many blocks as fit on the device at once; the rest of the batch is pulled from the queue
+    cudaError_t e = cudaFuncSetAttribute(solve_queue_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_queue_kernel<G, S>, kBlockThreads, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned resident = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)a.sm_count;
+    if (blocks_needed > resident) {
+      e = cudaMemsetAsync(a.queue_counter, 0, sizeof(unsigned), a.stream);
+      if (e != cudaSuccess) return e;
+      solve_queue_kernel<G, S><<<resident, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n,
+                                                                            a.out, a.twist, a.plan, a.queue_counter);
+      return cudaGetLastError();
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  constexpr int kInstPerBlock = kBlockThreads / G;
-  const unsigned grid = (a.n + kInstPerBlock - 1) / kInstPerBlock;
-  solve_kernel<G, S><<<grid, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
-                                                               a.twist, a.plan);
+  solve_kernel<G, S><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
+                                                                       a.twist, a.plan);
   return cudaGetLastError();
 }
 

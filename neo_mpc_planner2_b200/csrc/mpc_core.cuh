@@ -468,11 +468,6 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
 template <int S>
 NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2); }
 
-struct SolveOut {
-  float cost;
-  unsigned iters, evals, status;
-};
-
 template <int S>
 NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
   float pgmax = 0.0f;
@@ -487,132 +482,187 @@ NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc).
+// One lane group's solve of one optimizer() call (srv.py:349-403), split into
+//   prologue()  request -> per-instance constants, footprint cost, state row, start point   (srv.py:350-361)
+//   pass()      one iteration of the projected L-BFGS                                        (srv.py:363-364)
+//   epilogue()  low-pass, collision check, accel clamp, state, response                      (srv.py:366-402)
+// so that a kernel can either run one instance per group (solve_instance) or refill finished groups from a
+// work queue while the other groups of the warp keep iterating (solve_queue_kernel).
+//
+// Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc):
 //   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion; pg = x - Proj(x - g) is the
 //   projected gradient; the secant pairs are those of the map pg, so an active disc constraint contributes
-//   its curvature), Armijo backtracking along the projection arc on the true objective incl. the piecewise-
-//   constant costmap term; falls back to a projected-gradient step when the quasi-Newton arc fails.
-// u holds the start point on entry (any point; it is projected) and the solution on exit.
-// `valid` = this group owns an instance; invalid groups only take part in the warp-wide votes/shuffles.
-// The first pass through the loop body only evaluates the start point (one copy of the rollout code).
+//   its curvature), binding constraints frozen along the step, Armijo backtracking along the projection arc on
+//   the true objective incl. the piecewise-constant costmap term; falls back to a projected-gradient step when
+//   the quasi-Newton arc fails.  The first pass of an instance only evaluates its start point.
+// Every collective (shuffle / vote) in here is executed by all 32 lanes of the warp; per-group decisions are
+// predicates, never branches around a collective.
 // ---------------------------------------------------------------------------------------------------------
 template <int G, int S>
-NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Instance& I, float (*u)[3],
-                           float* hist, int stride, int lg, bool valid, SolveOut& out) {
-  constexpr int PAIR = 6 * S + 2;
-  const int m = P.m;
-  Forward<G, S> fw;
-  float g[S][3], d[S][3], xt[S][3], pg[S][3], r[S][3];
+struct Solver {
+  static constexpr int PAIR = 6 * S + 2;
+  // per-instance constants
+  Instance I;
+  float last[3];
+  float waiting;
+  bool latched, new_goal, fp_hit, stateful, has_instance;
+  // iterate
+  float u[S][3], g[S][3], pg[S][3];
+  float f, pgmax, gamma;
+  unsigned iters, evals, status;
+  int hist_len, head, small_steps;
+  bool active, force_pg, first;
 
-  NEOMPC_UNROLL
-  for (int j = 0; j < S; ++j) {
-    if (lg * S + j >= P.N) { u[j][0] = u[j][1] = u[j][2] = 0.0f; }
-    project_step(P, u[j][0], u[j][1], u[j][2]);
-    NEOMPC_UNROLL
-    for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; d[j][q] = 0.0f; pg[j][q] = 0.0f; }
+  NEOMPC_HD void prologue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
+                          float* hist, int stride) {
+    // (every lane of the warp runs the collective inside footprint_lethal, also for groups without an instance)
+    const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
+    init(P, rq, fp_any, valid, lg, hist, stride);
   }
-  for (int e = 0; e < m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
 
-  float f = 0.0f, pgmax = 0.0f;
-  unsigned iters = 0, evals = 0, status = NEOMPC_STATUS_MAXITER;
-  int hist_len = 0, head = 0;
-  float gamma = 1.0f;
-  bool active = valid;
-  bool force_pg = true;          // no curvature information yet
-  bool first = true;             // warp-uniform
-  int small_steps = 0;
+  // collective-free part of the prologue: may be executed by a subset of the groups of a warp
+  NEOMPC_HD void init(const SolverConst& P, const neompc_request& rq, bool fp_any, bool valid, int lg,
+                      float* hist, int stride) {
+    has_instance = valid;
+    I.cx = rq.carrot_x; I.cy = rq.carrot_y;
+    I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
+    I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
+    sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+    sincos_f(rq.pose_yaw, &I.st, &I.ct);
+    I.bx = I.by = 0; I.fx = I.fy = 0.0f;
+    if (P.cells != nullptr) {
+      // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
+      const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
+      const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
+      const double bxd = floor(gx), byd = floor(gy);
+      I.bx = (int)bxd; I.by = (int)byd;
+      I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
+    }
+    fp_hit = valid && fp_any;
+    const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
+    I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);        // srv.py:266,268 ; :262-263
 
-  while (true) {
-    bool qn_dir = false;
-    float alpha = 0.0f;
-    if (!first) {
-      // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
-      if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
-      if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
-      if (!Grp<G>::warp_any(active)) break;
-
-      // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
-      const bool use_qn = !force_pg && hist_len > 0;
+    // per-instance state and the new-goal reset (srv.py:358-361)
+    stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr && rq.instance_id < P.state_rows;
+    const float* row = stateful ? P.state + (size_t)rq.instance_id * P.state_stride : nullptr;
+    const float* tail = stateful ? row + 3 * P.N : nullptr;
+    last[0] = last[1] = last[2] = 0.0f;
+    waiting = 0.0f;
+    latched = false;
+    new_goal = true;
+    if (stateful) {
+      new_goal = !(tail[8] != 0.0f && tail[5] == rq.goal_x && tail[6] == rq.goal_y && tail[7] == rq.goal_yaw);
+      waiting = tail[3];
+      latched = tail[4] != 0.0f;
+      if (!new_goal) { last[0] = tail[0]; last[1] = tail[1]; last[2] = tail[2]; }
+      else waiting = 0.0f;
+    }
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      const bool ld = stateful && !new_goal && i < P.N;
+      u[j][0] = ld ? row[3 * i + 0] : 0.0f;          // warm start (srv.py:397-400) or zeros (srv.py:136,359)
+      u[j][1] = ld ? row[3 * i + 1] : 0.0f;
+      u[j][2] = ld ? row[3 * i + 2] : 0.0f;
+      project_step(P, u[j][0], u[j][1], u[j][2]);
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
+      for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
+    }
+    for (int e = 0; e < P.m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
+    f = 0.0f; pgmax = 0.0f; gamma = 1.0f;
+    iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
+    hist_len = 0; head = 0; small_steps = 0;
+    active = valid; force_pg = true; first = true;
+  }
+
+  // one iteration for every group of the warp (inactive groups compute and discard)
+  NEOMPC_HD void pass(const SolverConst& P, const CostTables& T, float* hist, int stride, int lg) {
+    const int m = P.m;
+    Forward<G, S> fw;
+    float d[S][3], xt[S][3], r[S][3];
+
+    // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
+    const bool use_qn = !first && !force_pg && hist_len > 0;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-      for (int k = 0; k < m; ++k) {
-        const bool on = use_qn && k < hist_len;
-        int p = head - 1 - k; if (p < 0) p += m;
-        float* sp = hist + (size_t)(p * PAIR) * stride;
-        const float* yp = sp + (size_t)(3 * S) * stride;
-        float dot = 0.0f;
-        NEOMPC_UNROLL
-        for (int e = 0; e < 3 * S; ++e) dot += sp[(size_t)e * stride] * r[e / 3][e % 3];
-        dot = Grp<G>::sum(dot);
-        const float a = on ? sp[(size_t)(6 * S) * stride] * dot : 0.0f;
-        sp[(size_t)(6 * S + 1) * stride] = a;
-        NEOMPC_UNROLL
-        for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
-      }
-      const float h0 = use_qn ? gamma : 1.0f;
+    for (int k = 0; k < m; ++k) {
+      const bool on = use_qn && k < hist_len;
+      int p = head - 1 - k; if (p < 0) p += m;
+      float* sp = hist + (size_t)(p * PAIR) * stride;
+      const float* yp = sp + (size_t)(3 * S) * stride;
+      float dot = 0.0f;
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
+      for (int e = 0; e < 3 * S; ++e) dot += sp[(size_t)e * stride] * r[e / 3][e % 3];
+      dot = Grp<G>::sum(dot);
+      const float a = on ? sp[(size_t)(6 * S) * stride] * dot : 0.0f;
+      sp[(size_t)(6 * S + 1) * stride] = a;
+      NEOMPC_UNROLL
+      for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
+    }
+    const float h0 = use_qn ? gamma : 1.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-      for (int k = m - 1; k >= 0; --k) {
-        const bool on = use_qn && k < hist_len;
-        int p = head - 1 - k; if (p < 0) p += m;
-        const float* sp = hist + (size_t)(p * PAIR) * stride;
-        const float* yp = sp + (size_t)(3 * S) * stride;
-        float dot = 0.0f;
-        NEOMPC_UNROLL
-        for (int e = 0; e < 3 * S; ++e) dot += yp[(size_t)e * stride] * r[e / 3][e % 3];
-        dot = Grp<G>::sum(dot);
-        const float b = on ? sp[(size_t)(6 * S + 1) * stride] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
-        NEOMPC_UNROLL
-        for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] += b * sp[(size_t)e * stride];
-      }
-      // d = -r; it must be a descent direction for the projected gradient, else restart from -pg
-      float gd = 0.0f, pgn2 = 0.0f;
+    for (int k = m - 1; k >= 0; --k) {
+      const bool on = use_qn && k < hist_len;
+      int p = head - 1 - k; if (p < 0) p += m;
+      const float* sp = hist + (size_t)(p * PAIR) * stride;
+      const float* yp = sp + (size_t)(3 * S) * stride;
+      float dot = 0.0f;
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) {
-        NEOMPC_UNROLL
-        for (int q = 0; q < 3; ++q) {
-          d[j][q] = -r[j][q];
-          gd += pg[j][q] * d[j][q];
-          pgn2 += pg[j][q] * pg[j][q];
-        }
-      }
-      gd = Grp<G>::sum(gd);
-      pgn2 = Grp<G>::sum(pgn2);
-      qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
-      // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
-      // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
-      // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
-      if (P.disc_only) {
-        NEOMPC_UNROLL
-        for (int j = 0; j < S; ++j) {
-          const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
-          const float gr = g[j][0] * u[j][0] + g[j][1] * u[j][1];
-          const bool bind = n2 >= P.R * P.R * (1.0f - 2e-6f) && gr < 0.0f;
-          const float dr = (d[j][0] * u[j][0] + d[j][1] * u[j][1]) / fmaxf(n2, 1e-30f);
-          d[j][0] -= bind ? dr * u[j][0] : 0.0f;
-          d[j][1] -= bind ? dr * u[j][1] : 0.0f;
-        }
-      }
+      for (int e = 0; e < 3 * S; ++e) dot += yp[(size_t)e * stride] * r[e / 3][e % 3];
+      dot = Grp<G>::sum(dot);
+      const float b = on ? sp[(size_t)(6 * S + 1) * stride] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) {
-        const bool at_lo = u[j][2] <= P.lo[2] && g[j][2] > 0.0f;
-        const bool at_hi = u[j][2] >= P.hi[2] && g[j][2] < 0.0f;
-        d[j][2] = (at_lo || at_hi) ? 0.0f : d[j][2];
-      }
-      alpha = 1.0f;
-      if (!qn_dir) {
-        NEOMPC_UNROLL
-        for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
-        // first trial moves the largest component by about the velocity range
-        alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+      for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] += b * sp[(size_t)e * stride];
+    }
+    // d = -r; it must be a descent direction for the projected gradient, else restart from -pg
+    float gd = 0.0f, pgn2 = 0.0f;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      NEOMPC_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        d[j][q] = -r[j][q];
+        gd += pg[j][q] * d[j][q];
+        pgn2 += pg[j][q] * pg[j][q];
       }
     }
+    gd = Grp<G>::sum(gd);
+    pgn2 = Grp<G>::sum(pgn2);
+    const bool qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
+    // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
+    // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
+    // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
+    if (P.disc_only) {
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
+        const float gr = g[j][0] * u[j][0] + g[j][1] * u[j][1];
+        const bool bind = n2 >= P.R * P.R * (1.0f - 2e-6f) && gr < 0.0f;
+        const float dr = (d[j][0] * u[j][0] + d[j][1] * u[j][1]) / fmaxf(n2, 1e-30f);
+        d[j][0] -= bind ? dr * u[j][0] : 0.0f;
+        d[j][1] -= bind ? dr * u[j][1] : 0.0f;
+      }
+    }
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const bool at_lo = u[j][2] <= P.lo[2] && g[j][2] > 0.0f;
+      const bool at_hi = u[j][2] >= P.hi[2] && g[j][2] < 0.0f;
+      d[j][2] = (at_lo || at_hi) ? 0.0f : d[j][2];
+    }
+    float alpha = 1.0f;
+    if (!qn_dir) {
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
+      // first trial moves the largest component by about the velocity range
+      alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+    }
+    if (first) alpha = 0.0f;                     // evaluate the start point itself
 
     // ---- Armijo backtracking along the projection arc (all groups of the warp in lock step)
     bool ls_done = !active, accepted = false;
@@ -656,7 +706,6 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
     const float pgmax_n = Grp<G>::max(projected_gradient<S>(P, xt, gn, pgn));
     // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
     // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
-    // (The reductions are warp collectives: every lane executes them, whatever its group decides below.)
     float sy = 0.0f, yy = 0.0f;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
@@ -704,155 +753,114 @@ NEOMPC_HD void lbfgs_solve(const SolverConst& P, const CostTables& T, const Inst
         active = false;                              // projected-gradient arc failed too
         status = NEOMPC_STATUS_LINESEARCH;
       }
+      // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
+      if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+      if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
     }
     first = false;
   }
-  out.cost = f;
-  out.iters = iters;
-  out.evals = evals;
-  out.status = status;
-}
 
-// ---------------------------------------------------------------------------------------------------------
-// One optimizer() call (srv.py:349-403) for the instance owned by this lane group.
-// ---------------------------------------------------------------------------------------------------------
-template <int G, int S>
-NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid,
-                              int lg, float* hist, int stride, neompc_response* resp, float* twist, float* plan) {
-  Instance I;
-  I.cx = rq.carrot_x; I.cy = rq.carrot_y;
-  I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
-  I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
-  sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
-  sincos_f(rq.pose_yaw, &I.st, &I.ct);
-  I.bx = I.by = 0; I.fx = I.fy = 0.0f;
-  if (P.cells != nullptr) {
-    // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
-    const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
-    const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
-    const double bxd = floor(gx), byd = floor(gy);
-    I.bx = (int)bxd; I.by = (int)byd;
-    I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
-  }
-  // (every lane of the warp runs the collective inside footprint_lethal, also for groups without an instance)
-  const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
-  const bool fp_hit = valid && fp_any;
-  {
-    const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
-    I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);        // srv.py:266,268 ; :262-263
-  }
-
-  // ---- per-instance state and the new-goal reset (srv.py:358-361)
-  const bool stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr &&
-                        rq.instance_id < P.state_rows;
-  float* row = stateful ? P.state + (size_t)rq.instance_id * P.state_stride : nullptr;
-  float* tail = stateful ? row + 3 * P.N : nullptr;
-  float last[3] = {0.0f, 0.0f, 0.0f};
-  float waiting = 0.0f;
-  bool latched = false;
-  bool new_goal = true;
-  if (stateful) {
-    new_goal = !(tail[8] != 0.0f && tail[5] == rq.goal_x && tail[6] == rq.goal_y && tail[7] == rq.goal_yaw);
-    waiting = tail[3];
-    latched = tail[4] != 0.0f;
-    if (!new_goal) { last[0] = tail[0]; last[1] = tail[1]; last[2] = tail[2]; }
-    else waiting = 0.0f;
-  }
-  float u[S][3];
-  NEOMPC_UNROLL
-  for (int j = 0; j < S; ++j) {
-    const int i = lg * S + j;
-    const bool ld = stateful && !new_goal && i < P.N;
-    u[j][0] = ld ? row[3 * i + 0] : 0.0f;
-    u[j][1] = ld ? row[3 * i + 1] : 0.0f;
-    u[j][2] = ld ? row[3 * i + 2] : 0.0f;
-  }
-
-  // ---- the solve (srv.py:363-364)
-  SolveOut so;
-  lbfgs_solve<G, S>(P, T, I, u, hist, stride, lg, valid, so);
-  const float j_true = so.cost + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
-  if (valid && plan != nullptr) {
+  // post-solve part of optimizer() (srv.py:365-402).  Executed by every lane of the warp (it contains collectives);
+  // only groups with `fin` set (a finished instance) write response / twist / plan / state.  Solver state is not
+  // modified, so groups that are still iterating pass through unharmed.
+  NEOMPC_HD void epilogue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool fin, int lg,
+                          neompc_response* resp, float* twist, float* plan) const {
+    const bool valid = has_instance && fin;
+    const float j_true = f + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
+    if (valid && plan != nullptr) {                   // the raw solution x.x (what publishLocalPlan gets, srv.py:365)
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        const int i = lg * S + j;
+        if (i < P.N) { plan[3 * i + 0] = u[j][0]; plan[3 * i + 1] = u[j][1]; plan[3 * i + 2] = u[j][2]; }
+      }
+    }
+    // ---- low-pass on the first control (srv.py:366-367; the reference does it in place on x.x)
+    float ue[S][3];
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { ue[j][0] = u[j][0]; ue[j][1] = u[j][1]; ue[j][2] = u[j][2]; }
+    if (lg == 0) {
+      NEOMPC_UNROLL
+      for (int q = 0; q < 3; ++q) ue[0][q] = ue[0][q] * P.lp_gain + last[q] * (1.0f - P.lp_gain);
+    }
+    // ---- collision_check: re-roll with the TRUE yaw (srv.py:312-347)
+    Forward<G, S> fw;
+    fw.rollout(P, ue, lg);
+    int hit = 0;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      const int i = lg * S + j;
-      if (i < P.N) { plan[3 * i + 0] = u[j][0]; plan[3 * i + 1] = u[j][1]; plan[3 * i + 2] = u[j][2]; }
+      const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
+      hit |= (lg * S + j < P.N) ? (T.flag[cell] >> 1) & 1 : 0;                          // col >= 0.99, srv.py:338
     }
-  }
-
-  // ---- low-pass on the first control, in place (srv.py:366-367)
-  if (lg == 0) {
-    NEOMPC_UNROLL
-    for (int q = 0; q < 3; ++q) u[0][q] = u[0][q] * P.lp_gain + last[q] * (1.0f - P.lp_gain);
-  }
-  // ---- collision_check: re-roll with the TRUE yaw (srv.py:312-347)
-  Forward<G, S> fw;
-  fw.rollout(P, u, lg);
-  int hit = 0;
-  NEOMPC_UNROLL
-  for (int j = 0; j < S; ++j) {
-    const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
-    hit |= (lg * S + j < P.N) ? (T.flag[cell] >> 1) & 1 : 0;                          // col >= 0.99, srv.py:338
-  }
-  hit = Grp<G>::imax(hit);
-  bool collision = latched || hit != 0;
-  float o[3];
+    hit = Grp<G>::imax(hit);
+    bool collision = latched || hit != 0;
+    float wait = waiting;
+    float o[3];
 #if defined(__CUDA_ARCH__)
-  o[0] = __shfl_sync(kFullMask, u[0][0], 0, G);
-  o[1] = __shfl_sync(kFullMask, u[0][1], 0, G);
-  o[2] = __shfl_sync(kFullMask, u[0][2], 0, G);
+    o[0] = __shfl_sync(kFullMask, ue[0][0], 0, G);
+    o[1] = __shfl_sync(kFullMask, ue[0][1], 0, G);
+    o[2] = __shfl_sync(kFullMask, ue[0][2], 0, G);
 #else
-  o[0] = u[0][0]; o[1] = u[0][1]; o[2] = u[0][2];
+    o[0] = ue[0][0]; o[1] = ue[0][1]; o[2] = ue[0][2];
 #endif
-  const float lp0 = o[0], lp1 = o[1], lp2 = o[2];
-  unsigned flags = 0;
-  if (collision || fp_hit) {                                                          // srv.py:374-382
-    o[0] = o[1] = o[2] = 0.0f;
-    flags |= NEOMPC_FLAG_STOPPED;
-    waiting += rq.delta_t;
-    if (waiting >= 3.0f) { collision = false; waiting = 0.0f; }
-  } else {                                                                            // srv.py:385-391
-    NEOMPC_UNROLL
-    for (int q = 0; q < 3; ++q) {
-      const float lim = P.acc[q] * rq.control_interval;
-      o[q] = fmaxf(fminf(o[q], last[q] + lim), last[q] - lim);
+    unsigned flags = 0;
+    if (collision || fp_hit) {                                                          // srv.py:374-382
+      o[0] = o[1] = o[2] = 0.0f;
+      flags |= NEOMPC_FLAG_STOPPED;
+      wait += rq.delta_t;
+      if (wait >= 3.0f) { collision = false; wait = 0.0f; }
+    } else {                                                                            // srv.py:385-391
+      NEOMPC_UNROLL
+      for (int q = 0; q < 3; ++q) {
+        const float lim = P.acc[q] * rq.control_interval;
+        o[q] = fmaxf(fminf(o[q], last[q] + lim), last[q] - lim);
+      }
     }
-  }
-  if (collision) flags |= NEOMPC_FLAG_COLLISION;
-  if (fp_hit) flags |= NEOMPC_FLAG_COLLISION_FOOTPRINT;
-  if (new_goal) flags |= NEOMPC_FLAG_NEW_GOAL;
-
-  if (!valid) return;
-  // ---- state: last_control (srv.py:393-395), warm start (srv.py:397-400), old_goal (srv.py:402)
-  if (stateful) {
-    const bool success = so.status != NEOMPC_STATUS_MAXITER;
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) {
-      const int i = lg * S + j;
-      if (i < P.N) {
-        // success: plan shifted left by one step, tail = low-passed first control (srv.py:198-202)
-        const int dst = success ? (i == 0 ? P.N - 1 : i - 1) : i;
-        row[3 * dst + 0] = u[j][0]; row[3 * dst + 1] = u[j][1]; row[3 * dst + 2] = u[j][2];
+    if (collision) flags |= NEOMPC_FLAG_COLLISION;
+    if (fp_hit) flags |= NEOMPC_FLAG_COLLISION_FOOTPRINT;
+    if (new_goal) flags |= NEOMPC_FLAG_NEW_GOAL;
+    if (!valid) return;
+    // ---- state: last_control (srv.py:393-395), warm start (srv.py:397-400), old_goal (srv.py:402)
+    if (stateful) {
+      float* row = P.state + (size_t)rq.instance_id * P.state_stride;
+      float* tail = row + 3 * P.N;
+      const bool success = status != NEOMPC_STATUS_MAXITER;
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        const int i = lg * S + j;
+        if (i < P.N) {
+          // success: plan shifted left by one step, tail = low-passed first control (srv.py:198-202)
+          const int dst = success ? (i == 0 ? P.N - 1 : i - 1) : i;
+          row[3 * dst + 0] = ue[j][0]; row[3 * dst + 1] = ue[j][1]; row[3 * dst + 2] = ue[j][2];
+        }
+      }
+      if (lg == 0) {
+        tail[0] = o[0]; tail[1] = o[1]; tail[2] = o[2];
+        tail[3] = wait;
+        tail[4] = collision ? 1.0f : 0.0f;
+        tail[5] = rq.goal_x; tail[6] = rq.goal_y; tail[7] = rq.goal_yaw;
+        tail[8] = 1.0f;
+        tail[9] = fp_hit ? 1.0f : 0.0f;
       }
     }
     if (lg == 0) {
-      tail[0] = o[0]; tail[1] = o[1]; tail[2] = o[2];
-      tail[3] = waiting;
-      tail[4] = collision ? 1.0f : 0.0f;
-      tail[5] = rq.goal_x; tail[6] = rq.goal_y; tail[7] = rq.goal_yaw;
-      tail[8] = 1.0f;
-      tail[9] = fp_hit ? 1.0f : 0.0f;
+      neompc_response rs;
+      rs.vx = o[0]; rs.vy = o[1]; rs.omega = o[2];
+      rs.cost = j_true;
+      rs.iters = iters; rs.evals = evals; rs.status = status; rs.flags = flags;
+      *resp = rs;
+      if (twist != nullptr) { twist[0] = o[0]; twist[1] = o[1]; twist[2] = o[2]; }
     }
   }
-  (void)lp0; (void)lp1; (void)lp2;
-  if (lg == 0) {
-    neompc_response rs;
-    rs.vx = o[0]; rs.vy = o[1]; rs.omega = o[2];
-    rs.cost = j_true;
-    rs.iters = so.iters; rs.evals = so.evals; rs.status = so.status; rs.flags = flags;
-    *resp = rs;
-    if (twist != nullptr) { twist[0] = o[0]; twist[1] = o[1]; twist[2] = o[2]; }
-  }
+};
+
+// One optimizer() call for the instance owned by this lane group (one instance per group per launch).
+template <int G, int S>
+NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid,
+                              int lg, float* hist, int stride, neompc_response* resp, float* twist, float* plan) {
+  Solver<G, S> sv;
+  sv.prologue(P, T, rq, valid, lg, hist, stride);
+  while (Grp<G>::warp_any(sv.active)) sv.pass(P, T, hist, stride, lg);
+  sv.epilogue(P, T, rq, true, lg, resp, twist, plan);
 }
 
 // objective value (reference J, unsmoothed) and gradient (smoothed objective) at a given u — test hook

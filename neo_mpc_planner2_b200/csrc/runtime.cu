@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -35,6 +36,9 @@ struct neompc_handle {
   neompc_optimizer_request* d_msgs = nullptr;
   size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
   uint64_t launches = 0;
+  unsigned* d_queue = nullptr;     // work-queue counter of the persistent solve kernel
+  int sm_count = 0;
+  bool use_queue = false;
   std::string err;
 };
 
@@ -171,6 +175,8 @@ int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, ne
   a.twist = d_twist;
   a.plan = d_plan;
   a.stream = s;
+  a.queue_counter = h->use_queue ? h->d_queue : nullptr;
+  a.sm_count = h->sm_count;
   cudaError_t e = dispatch(h, false, a);
   if (e != cudaSuccess) return cuda_fail(h, e, "solve kernel launch");
   h->launches += 1;
@@ -221,6 +227,9 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+  CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  h->use_queue = std::getenv("NEOMPC_USE_QUEUE") != nullptr;   // opt-in: measured slower (profiles/queue_vs_plain_r1.txt)
   CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_lut_flag, kTableSize + 6));
 #undef CREATE_CUDA
@@ -237,7 +246,7 @@ int neompc_destroy(neompc_handle* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
-  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
+  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs); cudaFree(h->d_queue);
   delete h;
   return NEOMPC_OK;
 }

@@ -245,6 +245,31 @@ def test_shard_invariance_and_determinism(Solver):
     assert np.concatenate([pa, pb]).tobytes() == plan.tobytes()
 
 
+def test_queue_kernel_matches_one_instance_per_group_kernel(Solver, monkeypatch):
+    """The opt-in persistent work-queue kernel (NEOMPC_USE_QUEUE=1, large batches) must return bit-identical results
+    to the default one-instance-per-group kernel."""
+    wl, p, cm = setup_workload("c3", 40000, 10)
+    req = wl.requests.copy()
+    req["instance_id"][:20000] = np.arange(20000, dtype=np.uint32)      # mix of stateful and stateless instances
+    outs = []
+    for use_queue in (True, False):
+        if use_queue:
+            monkeypatch.setenv("NEOMPC_USE_QUEUE", "1")
+        else:
+            monkeypatch.delenv("NEOMPC_USE_QUEUE", raising=False)
+        with Solver(wl.params) as s:
+            s.load_workload(wl)
+            s.reserve_instances(20000)
+            first = s.solve(req, want_plan=True)
+            second = s.solve(req, want_plan=True)                       # warm-started second tick
+            st = s.get_state(12345)
+        outs.append((first, second, st))
+    (a1, a2, sa), (b1, b2, sb) = outs
+    for x, y in ((a1, b1), (a2, b2)):
+        assert x[0].tobytes() == y[0].tobytes() and x[1].tobytes() == y[1].tobytes()
+    assert sa["initial_guess"].tobytes() == sb["initial_guess"].tobytes()
+
+
 def test_msgs_entry_matches_request_entry(Solver):
     from neo_mpc_planner2_b200.server import requests_to_msgs
     wl, p, cm = setup_workload("c2", 256, 3)
