@@ -80,7 +80,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     sample = args.cpu_sample or 64
     for _ in range(args.warmup):
         pass                                                     # pool warm-up happens inside cpu_reference_rate
@@ -300,12 +303,20 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            sample = args.cpu_sample or 96
-            rate, times, _ = cpu_reference_rate(args.config, sample, cores)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} problems of the same workload, cold start, scipy SLSQP "
-                                              f"as srv.py:363-364, multiprocessing.Pool({cores}), {times[0]:.1f} s"}
+            # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)
+            import subprocess
+            sample = args.cpu_sample or 256
+            env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config",
+                                  args.config, "--steps", "2", "--warmup", "1", "--cpu-sample", str(sample)],
+                                 capture_output=True, text=True, env=env, timeout=600)
+            try:
+                ref = json.loads(res.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+                line["cpu_baseline"]["sample"] += f", 2 timed passes, {ref['ms_per_step'] / 1e3:.1f} s each"
+            except Exception as exc:  # keep the GPU numbers even if the CPU arm failed
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"reference arm failed: {exc}: {res.stderr[-300:]}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

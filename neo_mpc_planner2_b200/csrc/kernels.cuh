@@ -63,6 +63,38 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 #endif
 constexpr int min_blocks_for(int S) { return S == 2 ? 5 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2; }
 
+// ---- TMA (bulk async copy) staging of the block's request tile ------------------------------------------------
+// The 128/G request records of a block are contiguous in HBM (64 B each): one elected thread arms an mbarrier with the
+// byte count and issues ONE cp.async.bulk (SASS: UBLKCP) global -> shared; every lane then reads its group's record
+// from shared memory instead of issuing four 16-byte global loads per lane.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_stage_requests(neompc_request* s_req, unsigned long long* mbar,
+                                                   const neompc_request* g_req, unsigned count) {
+  const uint32_t bar = smem_addr(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = count * (uint32_t)sizeof(neompc_request);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(s_req)), "l"(g_req), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+}
+
 template <int G, int S>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
 solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
@@ -73,10 +105,23 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   load_tables(st, lut_cost, lut_flag);
   CostTables T{st.cost, st.flag};
   constexpr int kInstPerBlock = kBlockThreads / G;
-  const unsigned inst = blockIdx.x * kInstPerBlock + threadIdx.x / G;
+  __shared__ alignas(128) neompc_request s_req[kInstPerBlock];
+  __shared__ alignas(8) unsigned long long s_mbar;
+  const unsigned first = blockIdx.x * kInstPerBlock;
+  const unsigned in_block = n - first < (unsigned)kInstPerBlock ? n - first : (unsigned)kInstPerBlock;
+  tma_stage_requests(s_req, &s_mbar, reqs + first, in_block);
+  const unsigned inst = first + threadIdx.x / G;
   const int lg = threadIdx.x % G;
   const bool valid = inst < n;
-  const neompc_request rq = load_request(reqs, inst, valid);
+  neompc_request rq;
+  {
+    float4* dst = reinterpret_cast<float4*>(&rq);
+    const float4* src = reinterpret_cast<const float4*>(&s_req[threadIdx.x / G]);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    dst[0] = valid ? src[0] : zero; dst[1] = valid ? src[1] : zero;
+    dst[2] = valid ? src[2] : zero; dst[3] = valid ? src[3] : zero;
+    if (!valid) rq.instance_id = NEOMPC_STATELESS;
+  }
   solve_instance<G, S>(P, T, rq, valid, lg, hist_smem + threadIdx.x, kBlockThreads,
                        valid ? out + inst : nullptr,
                        (valid && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,

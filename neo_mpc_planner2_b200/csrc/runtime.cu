@@ -165,6 +165,8 @@ int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, ne
                     float* d_twist, float* d_plan, cudaStream_t s) {
   if (n == 0) return NEOMPC_OK;
   if (n > 0xFFFFFFF0ull) return fail(h, NEOMPC_ERR_INVALID, "batch too large");
+  if ((reinterpret_cast<uintptr_t>(d_reqs) & 15u) != 0)      // the kernel stages request tiles with cp.async.bulk
+    return fail(h, NEOMPC_ERR_INVALID, "request array must be 16-byte aligned");
   LaunchArgs a{};
   a.P = h->c;
   a.lut_cost = h->d_lut_cost;
