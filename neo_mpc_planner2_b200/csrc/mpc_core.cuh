@@ -196,6 +196,15 @@ NEOMPC_HD float rsqrt_f(float v) {
 #endif
 }
 
+// a / b where a few ulp do not matter (step lengths, scalings): MUFU.RCP, no denormal slow path
+NEOMPC_HD float div_approx(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+
 NEOMPC_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -644,7 +653,7 @@ struct Solver {
         const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
         const float gr = g[j][0] * u[j][0] + g[j][1] * u[j][1];
         const bool bind = n2 >= P.R * P.R * (1.0f - 2e-6f) && gr < 0.0f;
-        const float dr = (d[j][0] * u[j][0] + d[j][1] * u[j][1]) / fmaxf(n2, 1e-30f);
+        const float dr = div_approx(d[j][0] * u[j][0] + d[j][1] * u[j][1], fmaxf(n2, 1e-30f));
         d[j][0] -= bind ? dr * u[j][0] : 0.0f;
         d[j][1] -= bind ? dr * u[j][1] : 0.0f;
       }
@@ -660,7 +669,7 @@ struct Solver {
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
       // first trial moves the largest component by about the velocity range
-      alpha = fmaxf(1.0f, P.R / fmaxf(pgmax, 1e-12f));
+      alpha = fmaxf(1.0f, div_approx(P.R, fmaxf(pgmax, 1e-12f)));
     }
     if (first) alpha = 0.0f;                     // evaluate the start point itself
 
@@ -690,7 +699,7 @@ struct Solver {
         if (gs >= 0.0f && bt == 0 && qn_dir) { ls_done = true; }
         // safeguarded quadratic interpolation of the step length
         const float denom = 2.0f * (ftrial - f - gs);
-        const float aq = denom > 0.0f ? -gs / denom : 0.5f;
+        const float aq = denom > 0.0f ? div_approx(-gs, denom) : 0.5f;
         alpha *= fminf(0.5f, fmaxf(0.1f, aq));
       }
     }
@@ -726,8 +735,8 @@ struct Solver {
             sp[(size_t)e * stride] = d[e / 3][e % 3];
             sp[(size_t)(3 * S + e) * stride] = r[e / 3][e % 3];
           }
-          sp[(size_t)(6 * S) * stride] = 1.0f / sy;
-          gamma = sy / yy;
+          sp[(size_t)(6 * S) * stride] = div_approx(1.0f, sy);
+          gamma = div_approx(sy, yy);
           head = head + 1 == m ? 0 : head + 1;
           hist_len = hist_len < m ? hist_len + 1 : m;
           force_pg = false;
