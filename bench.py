@@ -282,6 +282,13 @@ def run_ours(args):
         k_ms = float(np.mean(kern_ms))
         achieved = bytes_per_solve * n / (k_ms * 1e-3) / 1e9
         wl_name, _ = _workload_name(args.config)
+        traffic = None            # dram bytes per launch from the committed ncu capture of the same kernel/config
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
+            if tr and tr["kernel"] == f"solve_kernel<{G},{S}>" and tr["batch"] == n:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -293,7 +300,7 @@ def run_ours(args):
                        if world > 1 else "single GPU", "cold_start": True,
                        "iters_median": iters_med, "evals_mean": evals_mean},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
                          "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
                          "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * REQUEST_DTYPE.itemsize),
