@@ -8,7 +8,10 @@
 
 namespace neompc {
 
-constexpr int kBlockThreads = 128;      // 4 warps; 128/G instances per block
+#ifndef NEOMPC_BLOCK_THREADS
+#define NEOMPC_BLOCK_THREADS 64
+#endif
+constexpr int kBlockThreads = NEOMPC_BLOCK_THREADS;      // kBlockThreads/G instances per block
 constexpr int kMaxStepsPerLane = 6;
 
 struct LaunchArgs {
@@ -61,7 +64,10 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 #ifndef NEOMPC_MINBLOCKS_S3
 #define NEOMPC_MINBLOCKS_S3 4
 #endif
-constexpr int min_blocks_for(int S) { return S == 2 ? 5 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2; }
+// resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
+constexpr int min_blocks_for(int S) {
+  return (S == 2 ? 5 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2) * (128 / kBlockThreads);
+}
 
 // ---- TMA (bulk async copy) staging of the block's request tile ------------------------------------------------
 // The 128/G request records of a block are contiguous in HBM (64 B each): one elected thread arms an mbarrier with the

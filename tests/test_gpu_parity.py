@@ -283,6 +283,75 @@ def test_msgs_entry_matches_request_entry(Solver):
     assert np.abs(a["cost"] - b["cost"]).max() <= 1e-4 * max(1.0, np.abs(a["cost"]).max())
 
 
+def test_pack_requests_matches_reference_yaw_extraction(Solver):
+    """neompc_pack_requests (device, float64): euler_from_quaternion yaw for carrot / goal / current pose and the
+    goal-w quirk of srv.py:213, for arbitrary (also non-planar) unit quaternions."""
+    import torch
+    from neo_mpc_planner2_b200.abi import MSG_DTYPE
+    rng = np.random.default_rng(21)
+    n = 4096
+    msgs = np.zeros(n, MSG_DTYPE)
+    for name in ("carrot_pose", "goal_pose", "current_pose"):
+        q = rng.normal(size=(n, 4))
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        q[: n // 2, 0:2] = 0.0                                  # half of them planar (x = y = 0), re-normalised
+        q[: n // 2] /= np.linalg.norm(q[: n // 2], axis=1, keepdims=True)
+        msgs[name][:, 0:3] = rng.uniform(-20, 20, (n, 3))
+        msgs[name][:, 3:7] = q
+    msgs["current_vel"] = rng.uniform(-1, 1, (n, 6))
+    msgs["control_interval"] = 1.0 / 30.0
+    msgs["delta_t"] = rng.uniform(0, 1, n)
+    msgs["instance_id"] = np.arange(n)
+    with Solver(dict(control_steps=3)) as s:
+        d_msgs = torch.from_numpy(msgs.view(np.uint8).reshape(n, MSG_DTYPE.itemsize)).cuda()
+        d_reqs = torch.empty((n, REQUEST_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        s.pack_requests_device(d_msgs.data_ptr(), n, d_reqs.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        reqs = np.frombuffer(d_reqs.cpu().numpy().tobytes(), dtype=REQUEST_DTYPE)
+    def yaw(q):
+        return np.array([oracle.euler_yaw(*row) for row in q])
+    want = {
+        "carrot_yaw": yaw(msgs["carrot_pose"][:, 3:7]), "goal_yaw": yaw(msgs["goal_pose"][:, 3:7]),
+        "pose_yaw": yaw(msgs["current_pose"][:, 3:7]),
+        "pose_yaw_objective": np.array([oracle.quirk_yaw(msgs["current_pose"][i, 3:7], msgs["goal_pose"][i, 3:7])
+                                        for i in range(n)]),
+    }
+    for k, v in want.items():
+        d = np.abs(reqs[k].astype(np.float64) - v)
+        d = np.minimum(d, 2 * np.pi - d)                        # atan2 branch cut at +-pi
+        assert d.max() <= 4e-7, (k, d.max())
+    assert np.array_equal(reqs["vel_theta"], msgs["current_vel"][:, 5].astype(np.float32))
+    assert np.array_equal(reqs["pose_x"], msgs["current_pose"][:, 0].astype(np.float32))
+    assert np.array_equal(reqs["instance_id"], msgs["instance_id"])
+
+
+def test_parameter_and_costmap_updates_take_effect(Solver):
+    """neompc_set_params / neompc_set_costmap between solves (the reference's cb_params, srv.py:405-439, and the
+    costmap topic): later solves use the new values; control_steps may change too."""
+    wl, p, cm = setup_workload("c2", 128, 3)
+    rng = np.random.default_rng(3)
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        U = rng.uniform(-0.5, 0.5, (128, 9)).astype(np.float32)
+        J1 = s.eval_objective(wl.requests, U, want_grad=False)
+        s.set_params(wl.params, w_trans=0.3, w_costmap=0.5)
+        J2 = s.eval_objective(wl.requests, U, want_grad=False)
+        p2 = oracle.MpcParams(**dict(wl.params, w_trans=0.3, w_costmap=0.5))
+        fpl = footprint_lethal_flags(wl, cm)
+        Jo = oracle.objective_batch(p2, cm, wl.requests, U.astype(np.float64), fp_lethal=fpl)
+        edge = near_cell_edge(p2, cm, wl.requests, U.astype(np.float64))
+        assert not np.allclose(J1, J2)
+        assert (np.abs(J2 - Jo) / np.maximum(1, np.abs(Jo)))[~edge].max() <= 2e-5
+        s.set_costmap(None, 1.0, 0.0, 0.0)                       # free space
+        J3 = s.eval_objective(wl.requests, U, want_grad=False)
+        Jf = oracle.objective_batch(p2, None, wl.requests, U.astype(np.float64))
+        assert (np.abs(J3 - Jf) / np.maximum(1, np.abs(Jf))).max() <= 2e-5
+        s.set_params(wl.params, control_steps=7)
+        assert s.control_steps == 7
+        out, plan = s.solve(wl.requests, want_plan=True)
+        assert plan.shape == (128, 21) and feasibility_violation(dict(wl.params, control_steps=7), plan) <= 1e-6
+
+
 def test_full_size_properties(Solver):
     """BASELINE config C3 at full size (65536 x N=10): properties that need no oracle solve."""
     wl, p, cm = setup_workload("c3", None)
