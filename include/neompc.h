@@ -135,8 +135,9 @@ int neompc_set_params(neompc_handle* h, const neompc_params* params);
 int neompc_get_params(const neompc_handle* h, neompc_params* out);
 const char* neompc_last_error(const neompc_handle* h);   /* h may be NULL: last error of neompc_create on this thread */
 int neompc_version(void);
-/* sizeof() of the POD records as compiled, for binding self-checks: out[0..3] = request, response, params, optimizer_request */
-int neompc_abi_sizes(size_t out[4]);
+/* sizeof() of the POD records as compiled, for binding self-checks: out[0..5] = request, response, params, optimizer_request,
+ * robot_tick, carrot_info */
+int neompc_abi_sizes(size_t out[6]);
 
 /* ---- environment ------------------------------------------------------------------------------------------ */
 /* Costmap2d(self) (srv.py:118).  cells: row-major uint8 [height][width], copied to the device (host pointer).
@@ -176,6 +177,45 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
 /* Device-side packing only (d_msgs, d_reqs device pointers), asynchronous on `stream`. */
 int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n,
                          neompc_request* d_reqs, void* stream);
+
+/* ---- the step before the solve: carrot selection of the plugin ------------------- */
+/* One robot's inputs for one control tick: what computeVelocityCommands receives (cpp:202-205) plus the plugin state
+ * the reference keeps per instance (pruned plan position cpp:127, slow_down_ h:162).  48 bytes. */
+typedef struct neompc_robot_tick {
+  double pose_x, pose_y, pose_yaw;     /* robot pose in the plan / costmap global frame */
+  float vel_x, vel_y, vel_theta;       /* current speed (cpp:204) */
+  uint32_t plan_start;                 /* first plan pose still kept (the reference erases the ones before, cpp:127) */
+  uint32_t slow_down;                  /* slow_down_ (h:162), updated by cpp:216-232 */
+  float delta_t;                       /* forwarded to neompc_request.delta_t */
+} neompc_robot_tick;
+
+enum { NEOMPC_CARROT_OK = 0, NEOMPC_CARROT_EMPTY_WINDOW = 1 /* cpp:130-132 */, NEOMPC_CARROT_COLLISION = 2 /* cpp:234-236 */ };
+
+/* Per-robot result of the carrot selection.  16 bytes. */
+typedef struct neompc_carrot_info {
+  uint32_t status;            /* NEOMPC_CARROT_* */
+  uint32_t plan_start;        /* closest plan pose = new pruning position (cpp:81-86,127) */
+  uint32_t carrot_index;      /* plan pose chosen as carrot (cpp:173-189) */
+  uint32_t flags;             /* bit0 closer_to_goal (cpp:88-96), bit1 new slow_down_ (cpp:216-232), bits 8..15 footprint raw cost */
+} neompc_carrot_info;
+
+typedef struct neompc_carrot_params {
+  float lookahead_dist_min, lookahead_dist_max, lookahead_dist_close_to_goal;   /* cpp:311-323 */
+  float controller_frequency;                                                   /* cpp:323; control_interval = 1/f (cpp:246) */
+} neompc_carrot_params;
+
+/* setPlan (cpp:274-281): a global plan shared by all robots, poses (x, y, yaw) in the costmap's global frame; the
+ * last pose is the goal_pose of every request (cpp:280, :243).  Host pointer, copied. */
+int neompc_set_plan(neompc_handle* h, const double* xyyaw, size_t n_poses);
+/* transformGlobalPlan + getLookAheadDistance + getLookAheadPoint + slow-down hysteresis + request construction
+ * (cpp:66-135, 157-189, 216-246) for n robots: writes one neompc_request per robot (instance_id = first_instance_id + i,
+ * or NEOMPC_STATELESS when first_instance_id == NEOMPC_STATELESS) and one neompc_carrot_info.  Host buffers. */
+int neompc_build_requests(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* ticks, size_t n,
+                          uint32_t first_instance_id, neompc_request* reqs_out, neompc_carrot_info* info_out);
+/* Same on device buffers, asynchronous on `stream`; reqs_out can be passed straight to neompc_solve_batch_device. */
+int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* d_ticks,
+                                 size_t n, uint32_t first_instance_id, neompc_request* d_reqs_out,
+                                 neompc_carrot_info* d_info_out, void* stream);
 
 /* ---- test hooks ------------------------------------------------------------------------------------------- */
 /* objective(cmd_vel) (srv.py:204-269) and its analytic gradient for n (request, u) pairs; host buffers.

@@ -14,6 +14,7 @@ EXPORTS = [
     "neompc_version", "neompc_abi_sizes", "neompc_set_costmap", "neompc_set_costmap_device",
     "neompc_set_footprint", "neompc_reserve_instances", "neompc_reset_state", "neompc_get_state",
     "neompc_solve_batch", "neompc_solve_batch_device", "neompc_solve_msgs", "neompc_pack_requests",
+    "neompc_set_plan", "neompc_build_requests", "neompc_build_requests_device",
     "neompc_eval_objective", "neompc_launch_count", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
 ]
 
@@ -65,6 +66,9 @@ def load():
     lib.neompc_solve_batch_device.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     lib.neompc_solve_msgs.argtypes = [vp, vp, sz, vp, vp]
     lib.neompc_pack_requests.argtypes = [vp, vp, sz, vp, vp]
+    lib.neompc_set_plan.argtypes = [vp, vp, sz]
+    lib.neompc_build_requests.argtypes = [vp, vp, vp, sz, u32, vp, vp]
+    lib.neompc_build_requests_device.argtypes = [vp, vp, vp, sz, u32, vp, vp, vp]
     lib.neompc_eval_objective.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.neompc_launch_count.argtypes = [vp]
     lib.neompc_launch_count.restype = ctypes.c_uint64

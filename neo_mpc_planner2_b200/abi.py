@@ -45,6 +45,18 @@ MSG_DTYPE = np.dtype([
 ], align=False)
 assert MSG_DTYPE.itemsize == 240
 
+# neompc_robot_tick / neompc_carrot_info / neompc_carrot_params — carrot selection (cpp:66-246)
+TICK_DTYPE = np.dtype([
+    ("pose_x", "<f8"), ("pose_y", "<f8"), ("pose_yaw", "<f8"),
+    ("vel_x", "<f4"), ("vel_y", "<f4"), ("vel_theta", "<f4"),
+    ("plan_start", "<u4"), ("slow_down", "<u4"), ("delta_t", "<f4"),
+], align=False)
+assert TICK_DTYPE.itemsize == 48
+CARROT_INFO_DTYPE = np.dtype([("status", "<u4"), ("plan_start", "<u4"), ("carrot_index", "<u4"), ("flags", "<u4")])
+assert CARROT_INFO_DTYPE.itemsize == 16
+CARROT_PARAMS_DTYPE = np.dtype([("lookahead_dist_min", "<f4"), ("lookahead_dist_max", "<f4"),
+                                ("lookahead_dist_close_to_goal", "<f4"), ("controller_frequency", "<f4")])
+
 # neompc_response.status
 STATUS_CONVERGED = 0
 STATUS_MAXITER = 1

@@ -3,6 +3,7 @@
 // and MpcOptimizationServer.optimizer (reference neo_mpc_planner2/mpc_optimization_server.py:349-403).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "carrot.cuh"
 #include "kernels.cuh"
 #include "mpc_setup.h"
 
@@ -36,6 +38,14 @@ struct neompc_handle {
   neompc_optimizer_request* d_msgs = nullptr;
   size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
   uint64_t launches = 0;
+  // carrot selection (row N2): shared global plan, byte -> raw-cost table, staging
+  double* d_path = nullptr;
+  size_t path_len = 0, path_cap = 0;
+  uint8_t* d_raw_table = nullptr;
+  double resolution = 0.0;
+  neompc_robot_tick* d_ticks = nullptr;
+  neompc_carrot_info* d_info = nullptr;
+  size_t cap_ticks = 0;
   unsigned* d_queue = nullptr;     // work-queue counter of the persistent solve kernel
   int sm_count = 0;
   bool use_queue = false;
@@ -65,6 +75,18 @@ int upload_tables(neompc_handle* h) {
   build_tables(h->params, h->encoding, h->tab);
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_cost, h->tab.cost.data(), kTableSize * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_lut_flag, h->tab.flag.data(), kTableSize, cudaMemcpyHostToDevice, h->stream));
+  // costmap byte -> nav2 raw cost, for the plugin's footprintCostAtPose thresholds (cpp:218-236); occupancy grids are
+  // mapped back with the inverse of nav2's publisher table (oracle/carrot_oracle.py: raw_byte_table)
+  uint8_t raw[256];
+  for (int b = 0; b < 256; ++b) {
+    if (h->encoding == NEOMPC_ENC_NAV2_RAW) raw[b] = (uint8_t)b;
+    else if (b == 0) raw[b] = 0;
+    else if (b <= 98) raw[b] = (uint8_t)(1 + (int)std::floor((b - 1) * 251.0 / 97.0 + 0.5));
+    else if (b == 99) raw[b] = 253;
+    else if (b == 100) raw[b] = 254;
+    else raw[b] = 255;
+  }
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_raw_table, raw, 256, cudaMemcpyHostToDevice, h->stream));
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   return NEOMPC_OK;
 }
@@ -191,12 +213,14 @@ extern "C" {
 
 int neompc_version(void) { return NEOMPC_VERSION; }
 
-int neompc_abi_sizes(size_t out[4]) {
+int neompc_abi_sizes(size_t out[6]) {
   if (!out) return NEOMPC_ERR_INVALID;
   out[0] = sizeof(neompc_request);
   out[1] = sizeof(neompc_response);
   out[2] = sizeof(neompc_params);
   out[3] = sizeof(neompc_optimizer_request);
+  out[4] = sizeof(neompc_robot_tick);
+  out[5] = sizeof(neompc_carrot_info);
   return NEOMPC_OK;
 }
 
@@ -230,6 +254,7 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaMalloc(&h->d_queue, sizeof(unsigned)));
+  CREATE_CUDA(cudaMalloc(&h->d_raw_table, 256));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   h->use_queue = std::getenv("NEOMPC_USE_QUEUE") != nullptr;   // opt-in: measured slower (profiles/queue_vs_plain_r1.txt)
   CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
@@ -249,6 +274,7 @@ int neompc_destroy(neompc_handle* h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs); cudaFree(h->d_queue);
+  cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
   delete h;
   return NEOMPC_OK;
 }
@@ -305,6 +331,7 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
   h->c.inv_res_d = 1.0 / resolution;
   h->c.inv_res = (float)(1.0 / resolution);
   h->c.origin_x = origin_x; h->c.origin_y = origin_y;
+  h->resolution = resolution;
   if (encoding != h->encoding) {
     h->encoding = encoding;
     return upload_tables(h);
@@ -478,6 +505,78 @@ int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const fl
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d_u); cudaFree(d_J);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_objective");
+  return NEOMPC_OK;
+}
+
+int neompc_set_plan(neompc_handle* h, const double* xyyaw, size_t n_poses) {
+  if (!h || !xyyaw || n_poses == 0 || n_poses > 0x7fffffffu) return fail(h, NEOMPC_ERR_INVALID, "plan must have >= 1 pose");
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  if (n_poses > h->path_cap) {
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_path) cudaFree(h->d_path);
+    h->d_path = nullptr; h->path_cap = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_path, n_poses * 3 * sizeof(double)));
+    h->path_cap = n_poses;
+  }
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_path, xyyaw, n_poses * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->path_len = n_poses;
+  return NEOMPC_OK;
+}
+
+int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* d_ticks,
+                                 size_t n, uint32_t first_instance_id, neompc_request* d_reqs_out,
+                                 neompc_carrot_info* d_info_out, void* stream) {
+  if (!h || !cp || (n > 0 && (!d_ticks || !d_reqs_out || !d_info_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (h->path_len == 0) return fail(h, NEOMPC_ERR_INVALID, "no plan set (neompc_set_plan)");
+  if (!(cp->controller_frequency > 0.0f)) return fail(h, NEOMPC_ERR_INVALID, "controller_frequency must be > 0");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  CarrotConst c{};
+  c.plan = h->d_path;
+  c.L = (unsigned)h->path_len;
+  c.la_min = (double)cp->lookahead_dist_min;
+  c.la_max = (double)cp->lookahead_dist_max;
+  c.la_close = (double)cp->lookahead_dist_close_to_goal;
+  c.control_interval = 1.0f / cp->controller_frequency;
+  c.cells = h->c.cells;
+  c.W = h->c.W; c.H = h->c.H;
+  c.origin_x = h->c.origin_x; c.origin_y = h->c.origin_y;
+  c.resolution = h->resolution;
+  // max_transform_dist = max(size_x, size_y) * resolution / 2 (cpp:78-79); without a costmap every pose is inside
+  c.max_transform_dist = h->c.cells ? (double)(h->c.W > h->c.H ? h->c.W : h->c.H) * h->resolution / 2.0 : 1.0e300;
+  c.raw_table = h->d_raw_table;
+  c.fp_n = h->c.fp_n;
+  std::memcpy(c.fp_x, h->c.fp_x, sizeof(c.fp_x));
+  std::memcpy(c.fp_y, h->c.fp_y, sizeof(c.fp_y));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  cudaError_t e = launch_build_requests(c, d_ticks, (unsigned)n, first_instance_id, d_reqs_out, d_info_out, s);
+  if (e != cudaSuccess) return cuda_fail(h, e, "build_requests kernel launch");
+  h->launches += 1;
+  return NEOMPC_OK;
+}
+
+int neompc_build_requests(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* ticks, size_t n,
+                          uint32_t first_instance_id, neompc_request* reqs_out, neompc_carrot_info* info_out) {
+  if (!h || !cp || (n > 0 && (!ticks || !reqs_out || !info_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h, n, false, false);
+  if (rc != NEOMPC_OK) return rc;
+  if (n > h->cap_ticks) {
+    if (h->d_ticks) cudaFree(h->d_ticks);
+    if (h->d_info) cudaFree(h->d_info);
+    h->d_ticks = nullptr; h->d_info = nullptr; h->cap_ticks = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_ticks, n * sizeof(neompc_robot_tick)));
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_info, n * sizeof(neompc_carrot_info)));
+    h->cap_ticks = n;
+  }
+  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_ticks, ticks, n * sizeof(neompc_robot_tick), cudaMemcpyHostToDevice, h->stream));
+  rc = neompc_build_requests_device(h, cp, h->d_ticks, n, first_instance_id, h->d_reqs, h->d_info, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  NEOMPC_CUDA(h, cudaMemcpyAsync(reqs_out, h->d_reqs, n * sizeof(neompc_request), cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaMemcpyAsync(info_out, h->d_info, n * sizeof(neompc_carrot_info), cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   return NEOMPC_OK;
 }
 

@@ -10,7 +10,8 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .abi import (REQUEST_DTYPE, RESPONSE_DTYPE, PARAMS_DTYPE, MSG_DTYPE, ENC_OCCUPANCY, params_record)
+from .abi import (REQUEST_DTYPE, RESPONSE_DTYPE, PARAMS_DTYPE, MSG_DTYPE, ENC_OCCUPANCY, params_record,
+                  TICK_DTYPE, CARROT_INFO_DTYPE, CARROT_PARAMS_DTYPE, STATELESS)
 
 NeompcError = _lib.NeompcError
 
@@ -151,6 +152,39 @@ class BatchSolver:
     def pack_requests_device(self, d_msgs, n, d_reqs, stream=None):
         self._check(self._lib.neompc_pack_requests(self._h, ctypes.c_void_p(d_msgs), int(n), ctypes.c_void_p(d_reqs),
                                                    ctypes.c_void_p(stream) if stream else None), "neompc_pack_requests")
+
+    # ------------------------------------------------------------------ the step before: carrot selection (cpp:66-246)
+    def set_plan(self, xyyaw):
+        """setPlan (cpp:274-281): global plan poses (x, y, yaw), shared by all robots of this handle."""
+        plan = np.ascontiguousarray(np.asarray(xyyaw, dtype=np.float64).reshape(-1, 3))
+        self._check(self._lib.neompc_set_plan(self._h, _ptr(plan), len(plan)), "neompc_set_plan")
+
+    @staticmethod
+    def carrot_params(lookahead_dist_min=0.5, lookahead_dist_max=0.5, lookahead_dist_close_to_goal=0.5,
+                      controller_frequency=30.0):
+        cp = np.zeros((), CARROT_PARAMS_DTYPE)
+        cp["lookahead_dist_min"], cp["lookahead_dist_max"] = lookahead_dist_min, lookahead_dist_max
+        cp["lookahead_dist_close_to_goal"], cp["controller_frequency"] = lookahead_dist_close_to_goal, controller_frequency
+        return cp
+
+    def build_requests(self, ticks, carrot_params, first_instance_id=STATELESS):
+        """Carrot selection + request construction for n robots (neompc_build_requests, host buffers)."""
+        ticks = np.ascontiguousarray(ticks, dtype=TICK_DTYPE)
+        n = len(ticks)
+        reqs = np.empty(n, REQUEST_DTYPE)
+        info = np.empty(n, CARROT_INFO_DTYPE)
+        self._check(self._lib.neompc_build_requests(self._h, _ptr(carrot_params), _ptr(ticks), n,
+                                                    int(first_instance_id), _ptr(reqs), _ptr(info)),
+                    "neompc_build_requests")
+        return reqs, info
+
+    def build_requests_device(self, carrot_params, d_ticks, n, d_reqs, d_info, first_instance_id=STATELESS, stream=None):
+        if stream == 0:
+            stream = 1
+        self._check(self._lib.neompc_build_requests_device(
+            self._h, _ptr(carrot_params), ctypes.c_void_p(d_ticks), int(n), int(first_instance_id),
+            ctypes.c_void_p(d_reqs), ctypes.c_void_p(d_info), ctypes.c_void_p(stream) if stream else None),
+            "neompc_build_requests_device")
 
     def eval_objective(self, reqs, u, want_grad=True):
         reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)
