@@ -20,6 +20,7 @@ using namespace neompc;
 struct neompc_handle {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // second stream of the chunked host-buffer path
   neompc_params params{};
   SolverConst c{};
   HostTables tab;
@@ -253,6 +254,7 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   } while (0)
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CREATE_CUDA(cudaMalloc(&h->d_queue, sizeof(unsigned)));
   CREATE_CUDA(cudaMalloc(&h->d_raw_table, 256));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -272,6 +274,7 @@ int neompc_destroy(neompc_handle* h) {
   if (!h) return NEOMPC_OK;
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs); cudaFree(h->d_queue);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
@@ -437,14 +440,28 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
   NEOMPC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h, n, plan_or_null != nullptr, false);
   if (rc != NEOMPC_OK) return rc;
-  NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs, reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream));
-  rc = do_solve_device(h, h->d_reqs, n, h->d_resp, nullptr, plan_or_null ? h->d_plan : nullptr, h->stream);
-  if (rc != NEOMPC_OK) return rc;
-  NEOMPC_CUDA(h, cudaMemcpyAsync(out, h->d_resp, n * sizeof(neompc_response), cudaMemcpyDeviceToHost, h->stream));
-  if (plan_or_null)
-    NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null, h->d_plan, n * 3 * (size_t)h->params.control_steps * sizeof(float),
-                                   cudaMemcpyDeviceToHost, h->stream));
+  // Large batches are cut into chunks that alternate between two streams, so the H2D copy of one chunk, the solve of
+  // another and the D2H copy of a third overlap (the copy engines for the two directions and the SMs are independent).
+  // Problems are independent, so chunking does not change any result.
+  const size_t n3 = 3 * (size_t)h->params.control_steps;
+  const int chunks = n >= 16384 ? 4 : 1;
+  const size_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+  cudaStream_t streams[2] = {h->stream, chunks > 1 ? h->stream2 : h->stream};
+  for (int c = 0; c < chunks; ++c) {
+    const size_t lo = (size_t)c * per;
+    if (lo >= n) break;
+    const size_t cnt = n - lo < per ? n - lo : per;
+    cudaStream_t s = streams[c & 1];
+    NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs + lo, reqs + lo, cnt * sizeof(neompc_request), cudaMemcpyHostToDevice, s));
+    rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, nullptr, plan_or_null ? h->d_plan + lo * n3 : nullptr, s);
+    if (rc != NEOMPC_OK) return rc;
+    NEOMPC_CUDA(h, cudaMemcpyAsync(out + lo, h->d_resp + lo, cnt * sizeof(neompc_response), cudaMemcpyDeviceToHost, s));
+    if (plan_or_null)
+      NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null + lo * n3, h->d_plan + lo * n3, cnt * n3 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, s));
+  }
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (chunks > 1) NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream2));
   return NEOMPC_OK;
 }
 

@@ -270,6 +270,24 @@ def test_queue_kernel_matches_one_instance_per_group_kernel(Solver, monkeypatch)
     assert sa["initial_guess"].tobytes() == sb["initial_guess"].tobytes()
 
 
+def test_chunked_host_path_equals_device_path(Solver):
+    """neompc_solve_batch pipelines large batches in chunks over two streams; results must equal the single-launch
+    device path bit for bit."""
+    import torch
+    from neo_mpc_planner2_b200.abi import RESPONSE_DTYPE
+    wl, p, cm = setup_workload("c3", 40001, 10)
+    n = wl.batch
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        host = s.solve(wl.requests)
+        d_req = torch.from_numpy(wl.requests.view(np.uint8).reshape(n, 64)).cuda()
+        d_out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+        s.solve_device(d_req.data_ptr(), n, d_out.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        dev = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESPONSE_DTYPE)
+    assert host.tobytes() == dev.tobytes()
+
+
 def test_msgs_entry_matches_request_entry(Solver):
     from neo_mpc_planner2_b200.server import requests_to_msgs
     wl, p, cm = setup_workload("c2", 256, 3)
