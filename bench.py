@@ -39,6 +39,9 @@ L2_FLUSH_BYTES = 256 << 20
 _W = {}
 
 
+PER_GPU_BATCH = {"c2": 4096, "c3": 65536, "c4": 131072, "c5": 100000}
+
+
 def _cpu_init(cfg, batch, seed_off):
     os.environ["OMP_NUM_THREADS"] = "1"
     import oracle
@@ -66,7 +69,7 @@ def cpu_reference_rate(cfg, sample, cores, repeats=1):
     """solves/s of the reference algorithm on `sample` problems of the workload with `cores` processes."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg, max(sample, 64), 0)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg, PER_GPU_BATCH[cfg], 0)) as pool:
         pool.map(_cpu_solve, range(min(cores, sample)))          # warm the workers (imports, first call)
         times, last = [], None
         for _ in range(repeats):
@@ -84,18 +87,19 @@ def run_reference(args):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    sample = args.cpu_sample or 64
-    for _ in range(args.warmup):
-        pass                                                     # pool warm-up happens inside cpu_reference_rate
+    sample = args.cpu_sample or {"c2": 1024, "c3": 128, "c4": 32, "c5": 128}[args.config]
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.config, max(sample, 64), 0)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.config, args.batch or PER_GPU_BATCH[args.config], 0)) as pool:
         for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_solve, range(min(cores, sample)))
         t0 = time.perf_counter()
+        last = None
         for _ in range(args.steps):
-            pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
+            last = pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
         dt = time.perf_counter() - t0
+    if args.dump_ref and last:
+        np.savez(args.dump_ref, J=np.array([r[1] for r in last]), x=np.stack([r[2] for r in last]))
     value = args.steps * sample / dt
     wl_name, n_steps = _workload_name(args.config)
     line = {
@@ -187,7 +191,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    per_gpu = {"c2": 4096, "c3": 65536, "c4": 131072, "c5": 100000}[args.config]
+    per_gpu = PER_GPU_BATCH[args.config]
     if args.batch:
         per_gpu = args.batch
     # every rank: same map, its own slice of the request distribution (seeded by rank)
@@ -312,15 +316,40 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)
             import subprocess
-            sample = args.cpu_sample or 256
+            sample = args.cpu_sample or {"c2": 2048, "c3": 256, "c4": 64, "c5": 256}[args.config]   # ~15 core-seconds
             env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+            import tempfile
+            dump = os.path.join(tempfile.mkdtemp(prefix="neompc_ref_"), "ref.npz")
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config",
-                                  args.config, "--steps", "2", "--warmup", "1", "--cpu-sample", str(sample)],
+                                  args.config, "--steps", "2", "--warmup", "1", "--cpu-sample", str(sample),
+                                  "--batch", str(n), "--dump-ref", dump],
                                  capture_output=True, text=True, env=env, timeout=600)
             try:
                 ref = json.loads(res.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = ref["cpu_baseline"]
                 line["cpu_baseline"]["sample"] += f", 2 timed passes, {ref['ms_per_step'] / 1e3:.1f} s each"
+                # cost residual J_gpu - J_scipy on the same problems (BASELINE.json metric), both evaluated by the
+                # float64 oracle objective at the respective solutions (untimed; checker use of oracle/)
+                import oracle
+                from oracle.costmap import GridCostmap
+                from oracle.mpc_oracle import footprint_world
+                refd = np.load(dump)
+                k = len(refd["J"])
+                sub = wl.requests[:k]
+                _, plan = solver.solve(sub, want_plan=True)
+                pm = oracle.MpcParams(**wl.params)
+                cm = GridCostmap(wl.cells, wl.resolution, wl.origin_x, wl.origin_y) if wl.cells is not None else None
+                fpl = np.array([cm.getFootprintCost(footprint_world(wl.footprint, float(r["pose_x"]), float(r["pose_y"]),
+                                float(r["pose_yaw"]))) == 1.0 for r in sub]) if cm is not None else None
+                Jg = oracle.objective_batch(pm, cm, sub, plan.astype(np.float64), fp_lethal=fpl)
+                dJ = Jg - refd["J"]
+                du = np.abs(plan[:, :3].astype(np.float64) - refd["x"][:, :3]).max(axis=1)
+                line["cost_residual"] = {
+                    "definition": "J_gpu - J_scipy(ftol=opt_tolerance), float64 oracle objective, same problems",
+                    "problems": int(k), "median": float(np.median(dJ)), "p99": float(np.percentile(dJ, 99)),
+                    "max": float(dJ.max()), "frac_worse_than_1e-4": float((dJ > 1e-4).mean()),
+                    "first_control_abs_diff_median": float(np.median(du)),
+                    "first_control_abs_diff_p90": float(np.percentile(du, 90))}
             except Exception as exc:  # keep the GPU numbers even if the CPU arm failed
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"reference arm failed: {exc}: {res.stderr[-300:]}"}
@@ -342,6 +371,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per instance (0 = auto)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ref", default="", help="reference arm: save per-problem J and x of the last pass (npz)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
