@@ -119,15 +119,17 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   const unsigned inst = first + threadIdx.x / G;
   const int lg = threadIdx.x % G;
   const bool valid = inst < n;
-  neompc_request rq;
-  {
-    float4* dst = reinterpret_cast<float4*>(&rq);
-    const float4* src = reinterpret_cast<const float4*>(&s_req[threadIdx.x / G]);
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    dst[0] = valid ? src[0] : zero; dst[1] = valid ? src[1] : zero;
-    dst[2] = valid ? src[2] : zero; dst[3] = valid ? src[3] : zero;
-    if (!valid) rq.instance_id = NEOMPC_STATELESS;
+  // The record stays in shared memory: the solver core reads fields from there when it needs them (prologue and
+  // epilogue) instead of holding 16 registers for the whole solve.  Slots past the end of the batch are zeroed.
+  if (in_block < (unsigned)kInstPerBlock) {
+    if (!valid && lg == 0) {
+      float4* dst = reinterpret_cast<float4*>(&s_req[threadIdx.x / G]);
+      dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s_req[threadIdx.x / G].instance_id = NEOMPC_STATELESS;
+    }
+    __syncthreads();
   }
+  const neompc_request& rq = s_req[threadIdx.x / G];
   solve_instance<G, S>(P, T, rq, valid, lg, hist_smem + threadIdx.x, kBlockThreads,
                        valid ? out + inst : nullptr,
                        (valid && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,

@@ -40,7 +40,8 @@
 namespace neompc {
 
 constexpr int kMaxMemory = 8;          // compile-time cap of L-BFGS pairs
-constexpr int kMaxBacktracks = 12;     // arc-search halvings per iteration
+constexpr int kMaxBacktracks = 8;      // arc-search trials per iteration (each shrinks the step by 0.1 .. 0.5)
+constexpr float kPinnedAlpha = 0.01f;  // two accepted steps in a row this short: the arc is pinned at a costmap cell edge
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kCellOob = 256;          // cost-table index of "outside the map" (cost 1.0, lethal)
 constexpr int kCellFree = 257;         // cost-table index of "no costmap loaded" (cost 0)
@@ -69,6 +70,10 @@ struct SolverConst {
   float lp_gain;       // low_pass_gain (srv.py:366-367)
   float tol_pg;        // projected-gradient tolerance derived from opt_tolerance
   float tol_f;         // relative objective-decrease tolerance derived from opt_tolerance
+  float pair_eps;      // curvature pairs with s.y <= pair_eps * y.y are skipped
+  float pin_alpha;     // an accepted arc parameter this small counts likewise (kPinnedAlpha)
+  float tol_x;         // an accepted step shorter than this (sup norm) counts as "the objective stopped moving"
+  int precond;         // 1: block-diagonal initial inverse Hessian in the two-loop recursion (Solver::precondition); 0: gamma I
   // costmap (Costmap2d, srv.py:118)
   const uint8_t* cells;   // device pointer or nullptr (free space)
   int W, H;
@@ -280,11 +285,40 @@ struct Instance {
   float tyaw, fyaw;      // target_yaw, final_yaw              (srv.py:211-212)
   float v0x, v0y, v0z;   // current velocity                   (srv.py:216-218)
   float cq, sq;          // cos/sin of pose_yaw_objective      (srv.py:213, hoisted from :234-236)
-  float ct, st;          // cos/sin of the true pose yaw       (srv.py:317)
   int bx, by;            // cell containing the current position
   float fx, fy;          // fractional position inside that cell, in cells
-  float jconst;          // terms that do not depend on u: terminal distance (srv.py:266) + footprint (srv.py:262-263)
 };
+
+// terms of J that do not depend on u: terminal distance (srv.py:266) + footprint (srv.py:262-263)
+NEOMPC_HD float constant_cost(const SolverConst& P, const neompc_request& rq, bool fp_hit) {
+  const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
+  return P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);
+}
+
+// What optimizer() remembers about an instance between calls (srv.py:115-117,138,146-149), read from its state row.
+struct Carry {
+  float last[3];         // last_control                       (srv.py:393-395)
+  float waiting;         // waiting_time                       (srv.py:378-382)
+  bool latched;          // self.collision                     (srv.py:338-339)
+  bool new_goal;         // goal_pose != old_goal              (srv.py:358-361)
+  bool stateful;
+};
+
+NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool valid) {
+  Carry c;
+  c.stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr && rq.instance_id < P.state_rows;
+  c.last[0] = c.last[1] = c.last[2] = 0.0f;
+  c.waiting = 0.0f;
+  c.latched = false;
+  c.new_goal = true;
+  if (c.stateful) {
+    const float* tail = P.state + (size_t)rq.instance_id * P.state_stride + 3 * P.N;
+    c.new_goal = !(tail[8] != 0.0f && tail[5] == rq.goal_x && tail[6] == rq.goal_y && tail[7] == rq.goal_yaw);
+    c.latched = tail[4] != 0.0f;
+    if (!c.new_goal) { c.last[0] = tail[0]; c.last[1] = tail[1]; c.last[2] = tail[2]; c.waiting = tail[3]; }
+  }
+  return c;
+}
 
 template <int G, int S>
 struct Forward {
@@ -512,15 +546,13 @@ struct Solver {
   static constexpr int PAIR = 6 * S + 2;
   // per-instance constants
   Instance I;
-  float last[3];
-  float waiting;
-  bool latched, new_goal, fp_hit, stateful, has_instance;
+  bool fp_hit, has_instance;
   // iterate
   float u[S][3], g[S][3], pg[S][3];
   float f, pgmax, gamma;
   unsigned iters, evals, status;
   int hist_len, head, small_steps;
-  bool active, force_pg, first;
+  bool active, force_pg, plain, first;
 
   NEOMPC_HD void prologue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
                           float* hist, int stride) {
@@ -537,7 +569,6 @@ struct Solver {
     I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
     I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
     sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
-    sincos_f(rq.pose_yaw, &I.st, &I.ct);
     I.bx = I.by = 0; I.fx = I.fy = 0.0f;
     if (P.cells != nullptr) {
       // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
@@ -548,24 +579,11 @@ struct Solver {
       I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
     }
     fp_hit = valid && fp_any;
-    const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
-    I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);        // srv.py:266,268 ; :262-263
 
-    // per-instance state and the new-goal reset (srv.py:358-361)
-    stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr && rq.instance_id < P.state_rows;
+    // per-instance state and the new-goal reset (srv.py:358-361); the epilogue reads the row again
+    const Carry cr = load_carry(P, rq, valid);
+    const bool stateful = cr.stateful, new_goal = cr.new_goal;
     const float* row = stateful ? P.state + (size_t)rq.instance_id * P.state_stride : nullptr;
-    const float* tail = stateful ? row + 3 * P.N : nullptr;
-    last[0] = last[1] = last[2] = 0.0f;
-    waiting = 0.0f;
-    latched = false;
-    new_goal = true;
-    if (stateful) {
-      new_goal = !(tail[8] != 0.0f && tail[5] == rq.goal_x && tail[6] == rq.goal_y && tail[7] == rq.goal_yaw);
-      waiting = tail[3];
-      latched = tail[4] != 0.0f;
-      if (!new_goal) { last[0] = tail[0]; last[1] = tail[1]; last[2] = tail[2]; }
-      else waiting = 0.0f;
-    }
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
@@ -581,7 +599,37 @@ struct Solver {
     f = 0.0f; pgmax = 0.0f; gamma = 1.0f;
     iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
     hist_len = 0; head = 0; small_steps = 0;
-    active = valid; force_pg = true; first = true;
+    active = valid; force_pg = true; plain = false; first = true;
+  }
+
+  // r <- H0 r where H0 is the inverse of a block-diagonal majorant of the model Hessian at u.  Per step i:
+  //   diag(av, av, aw) + k (I - q rr^T),   r = u_i - v0,  q = 1/(|r|^2 + eps^2),  k = (w_control/N) sqrt(q)
+  // k(...) is the exact Hessian of the smoothed control term (srv.py:253-254), which dominates at the README weights.
+  // av, aw bound the tracking terms (srv.py:250-252, 267-268): their Hessian in the step velocities is
+  // 2 a dt^2 M (x) R_k^T R_l with M_kl = N - max(k,l) (positions are cumulative sums of the steps); M has positive
+  // entries, so diag(row sums of M) - M is diagonally dominant, i.e. the row sums majorise it:
+  //   rowsum_i = (N-i)(i+1) + (N-i-1)(N-i)/2,  av = 2 (w_trans/N) dt^2 rowsum_i,
+  //   aw = 2 (w_orient/N) dt^2 rowsum_i + 2 w_orient w_terminal dt^2 N.
+  // The 3x3 block is inverted in closed form (Sherman-Morrison).  `on` = false leaves r unchanged (predicated).
+  NEOMPC_HD void precondition(const SolverConst& P, int lg, bool on, float (*r)[3]) const {
+    const float dt2 = 2.0f * P.dt * P.dt;
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) {
+      const int i = lg * S + j;
+      const float rowsum = (float)((P.N - i) * (i + 1) + ((P.N - i - 1) * (P.N - i)) / 2);
+      const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
+      const float q = div_approx(1.0f, rx * rx + ry * ry + rz * rz + P.eps2);
+      const float k = P.w_ctrl * sqrtf(q);
+      const float iv = div_approx(1.0f, dt2 * P.a_trans * rowsum + k);
+      const float iw = div_approx(1.0f, dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N) + k);
+      const float tx = iv * rx, ty = iv * ry, tz = iw * rz;
+      const float kq = k * q;
+      const float den = 1.0f - kq * (rx * tx + ry * ty + rz * tz);
+      const float c = div_approx(kq * (tx * r[j][0] + ty * r[j][1] + tz * r[j][2]), den);
+      r[j][0] = on ? iv * r[j][0] + c * tx : r[j][0];
+      r[j][1] = on ? iv * r[j][1] + c * ty : r[j][1];
+      r[j][2] = on ? iw * r[j][2] + c * tz : r[j][2];
+    }
   }
 
   // one iteration for every group of the warp (inactive groups compute and discard)
@@ -611,9 +659,14 @@ struct Solver {
       NEOMPC_UNROLL
       for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
     }
-    const float h0 = use_qn ? gamma : 1.0f;
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
+    const bool use_pc = P.precond != 0 && !plain;
+    const float h0 = P.precond ? 1.0f : (use_qn ? gamma : 1.0f);
+    if (P.precond) {
+      precondition(P, lg, use_pc, r);
+    } else {
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -643,7 +696,7 @@ struct Solver {
     }
     gd = Grp<G>::sum(gd);
     pgn2 = Grp<G>::sum(pgn2);
-    const bool qn_dir = use_qn && (gd < -1e-4f * pgn2 * h0);
+    const bool qn_dir = (use_qn || use_pc) && (gd < -1e-4f * pgn2 * h0);
     // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
     // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
     // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
@@ -688,6 +741,7 @@ struct Solver {
       }
       gs = Grp<G>::sum(gs);
       const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg));
+      NEOMPC_TRACE("   trial bt %d alpha %.4g gs %.4e df %.4e gd %.4e\n", bt, alpha, gs, ftrial - f, gd);
       if (!ls_done) {
         ++evals;
         ft = ftrial;
@@ -715,20 +769,21 @@ struct Solver {
     const float pgmax_n = Grp<G>::max(projected_gradient<S>(P, xt, gn, pgn));
     // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
     // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
-    float sy = 0.0f, yy = 0.0f;
+    float sy = 0.0f, yy = 0.0f, smax = 0.0f;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) {
         const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pg[j][q];
         sy += sv * yv; yy += yv * yv;
+        smax = fmaxf(smax, fabsf(sv));
         d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
       }
     }
-    sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy);
+    sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy); smax = Grp<G>::max(smax);
     if (active) {
       if (accepted) {
-        if (!first && sy > 1e-10f * yy && yy > 0.0f) {
+        if (!first && sy > P.pair_eps * yy && yy > 0.0f) {
           float* sp = hist + (size_t)(head * PAIR) * stride;
           NEOMPC_UNROLL
           for (int e = 0; e < 3 * S; ++e) {
@@ -740,6 +795,7 @@ struct Solver {
           head = head + 1 == m ? 0 : head + 1;
           hist_len = hist_len < m ? hist_len + 1 : m;
           force_pg = false;
+          plain = false;
         }
         const float df = f - ft;
         NEOMPC_UNROLL
@@ -752,11 +808,16 @@ struct Solver {
         if (!first) {
           ++iters;
           // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
-          if (df <= P.tol_f * fmaxf(1.0f, fabsf(f))) ++small_steps; else small_steps = 0;
+          // (a step that short means the arc search is pinned at a costmap cell edge)
+          if (df <= P.tol_f * fmaxf(1.0f, fabsf(f)) || smax <= P.tol_x || alpha <= P.pin_alpha) ++small_steps;
+          else small_steps = 0;
           if (small_steps >= 2) { active = false; status = NEOMPC_STATUS_CONVERGED; }
         }
+      } else if (qn_dir && use_qn) {
+        hist_len = 0; head = 0; force_pg = true;    // quasi-Newton arc failed: restart without history
+        ++iters;
       } else if (qn_dir) {
-        hist_len = 0; head = 0; force_pg = true;    // quasi-Newton arc failed: restart with projected gradient
+        plain = true;                                // the preconditioned arc failed as well: plain projected gradient
         ++iters;
       } else {
         active = false;                              // projected-gradient arc failed too
@@ -775,7 +836,12 @@ struct Solver {
   NEOMPC_HD void epilogue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool fin, int lg,
                           neompc_response* resp, float* twist, float* plan) const {
     const bool valid = has_instance && fin;
-    const float j_true = f + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
+    const float j_true = f + unsmooth_correction<G, S>(P, I, u, lg) + constant_cost(P, rq, fp_hit);
+    const Carry cr = load_carry(P, rq, valid);
+    const float* last = cr.last;
+    const bool stateful = cr.stateful, new_goal = cr.new_goal;
+    float ct, st;                                      // cos/sin of the true pose yaw (srv.py:317)
+    sincos_f(rq.pose_yaw, &st, &ct);
     if (valid && plan != nullptr) {                   // the raw solution x.x (what publishLocalPlan gets, srv.py:365)
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) {
@@ -797,12 +863,12 @@ struct Solver {
     int hit = 0;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      const int cell = Forward<G, S>::cell_of(P, I, I.ct, I.st, fw.x[j], fw.y[j]);
+      const int cell = Forward<G, S>::cell_of(P, I, ct, st, fw.x[j], fw.y[j]);
       hit |= (lg * S + j < P.N) ? (T.flag[cell] >> 1) & 1 : 0;                          // col >= 0.99, srv.py:338
     }
     hit = Grp<G>::imax(hit);
-    bool collision = latched || hit != 0;
-    float wait = waiting;
+    bool collision = cr.latched || hit != 0;
+    float wait = cr.waiting;
     float o[3];
 #if defined(__CUDA_ARCH__)
     o[0] = __shfl_sync(kFullMask, ue[0][0], 0, G);
@@ -881,7 +947,6 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
   I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
   I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
   sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
-  sincos_f(rq.pose_yaw, &I.st, &I.ct);
   I.bx = I.by = 0; I.fx = I.fy = 0.0f;
   if (P.cells != nullptr) {
     const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
@@ -892,8 +957,6 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
   }
   const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
   const bool fp_hit = valid && fp_any;
-  const float ddx = rq.carrot_x - rq.goal_x, ddy = rq.carrot_y - rq.goal_y;
-  I.jconst = P.wt_term * (ddx * ddx + ddy * ddy) + (fp_hit ? P.w_fp : 0.0f);
   float u[S][3], g[S][3];
   NEOMPC_UNROLL
   for (int j = 0; j < S; ++j) {
@@ -905,7 +968,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
   }
   Forward<G, S> fw;
   const float f = Grp<G>::sum(fw.run(P, T, I, u, lg));
-  const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + I.jconst;
+  const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + constant_cost(P, rq, fp_hit);
   fw.backward(P, I, u, lg, g);
   if (!valid) return;
   if (lg == 0) *Jout = jt;

@@ -67,14 +67,16 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
 // Solver tolerances derived from the reference's opt_tolerance (SLSQP's ftol there).  See DESIGN.md
 // "Meaning of opt_tolerance": the projected-gradient sup-norm must fall below kPgScale * opt_tolerance, or the
 // objective must stop decreasing by more than kFScale * opt_tolerance (relative) twice in a row.
-constexpr float kPgScale = 0.05f;
-constexpr float kFScale = 1e-3f;
+constexpr float kPgScale = 0.1f;
+constexpr float kFScale = 2e-3f;
+constexpr float kXScale = 0.1f;
 
 inline void build_const(const neompc_params& p, SolverConst& c) {
   std::memset(&c, 0, sizeof(c));
   const int N = p.control_steps;
   c.N = N;
-  c.m = p.lbfgs_memory > 0 ? p.lbfgs_memory : 3;   // iterations do not drop with more pairs (profiles/lbfgs_memory_r1.txt)
+  // with the block-diagonal preconditioner one pair does as well as 3 or 6 (profiles/solver_tuning_r1.txt)
+  c.m = p.lbfgs_memory > 0 ? p.lbfgs_memory : 1;
   c.max_iter = p.max_iterations > 0 ? p.max_iterations : 100;
   c.dt = p.prediction_horizon / (float)N;
   c.a_trans = p.w_trans / (float)N;
@@ -94,6 +96,10 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.lp_gain = p.low_pass_gain;
   c.tol_pg = kPgScale * p.opt_tolerance;
   c.tol_f = kFScale * p.opt_tolerance;
+  c.tol_x = kXScale * p.opt_tolerance;
+  c.precond = 1;
+  c.pin_alpha = kPinnedAlpha;
+  c.pair_eps = 1e-10f;
   c.cells = nullptr;
   c.state = nullptr;
   c.state_stride = state_stride_for(N);
