@@ -195,20 +195,25 @@ NEOMPC_HD void sincos_heading(bool fast, float a, float* s, float* c) {
 
 NEOMPC_HD float rsqrt_f(float v) {
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(v);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));   // one MUFU.RSQ; callers keep v in the normal range
+  return r;
 #else
   return 1.0f / sqrtf(v);
 #endif
 }
 
 // a / b where a few ulp do not matter (step lengths, scalings): MUFU.RCP, no denormal slow path
-NEOMPC_HD float div_approx(float a, float b) {
+NEOMPC_HD float rcp_approx(float b) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(a, b);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));     // one MUFU.RCP
+  return r;
 #else
-  return a / b;
+  return 1.0f / b;
 #endif
 }
+NEOMPC_HD float div_approx(float a, float b) { return a * rcp_approx(b); }
 
 NEOMPC_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
@@ -284,7 +289,7 @@ struct Instance {
   float cx, cy;          // carrot position                    (srv.py:219)
   float tyaw, fyaw;      // target_yaw, final_yaw              (srv.py:211-212)
   float v0x, v0y, v0z;   // current velocity                   (srv.py:216-218)
-  float cq, sq;          // cos/sin of pose_yaw_objective      (srv.py:213, hoisted from :234-236)
+  float cq, sq;          // cos/sin of pose_yaw_objective / resolution  (srv.py:213, hoisted from :234-236)
   int bx, by;            // cell containing the current position
   float fx, fy;          // fractional position inside that cell, in cells
 };
@@ -328,12 +333,18 @@ struct Forward {
   // 0..255 = the cell byte, kCellOob = outside the map, kCellFree = no costmap loaded.  Branch-free.
   static NEOMPC_HD int cell_of(const SolverConst& P, const Instance& I, float cr, float sr, float x, float y) {
     if (P.cells == nullptr) return kCellFree;                  // uniform
-    const float gx = I.fx + (cr * x - sr * y) * P.inv_res;
-    const float gy = I.fy + (sr * x + cr * y) * P.inv_res;
+    // (cr, sr) = cos/sin of the start yaw pre-multiplied by 1/resolution
+    const float gx = I.fx + (cr * x - sr * y);
+    const float gy = I.fy + (sr * x + cr * y);
+#if defined(__CUDA_ARCH__)
+    const int mx = I.bx + __float2int_rd(gx);
+    const int my = I.by + __float2int_rd(gy);
+#else
     const int mx = I.bx + (int)floorf(gx);
     const int my = I.by + (int)floorf(gy);
+#endif
     const bool inb = (unsigned)mx < (unsigned)P.W && (unsigned)my < (unsigned)P.H;
-    const size_t idx = inb ? (size_t)my * P.W + mx : 0;
+    const unsigned idx = inb ? (unsigned)my * (unsigned)P.W + (unsigned)mx : 0u;      // W*H < 2^32 (set_costmap checks)
 #if defined(__CUDA_ARCH__)
     const int cell = (int)__ldg(P.cells + idx);
 #else
@@ -509,7 +520,7 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
 // Per pair p (0..m-1): [3S floats s][3S floats y][rho][alpha scratch of the two-loop recursion]
 // ---------------------------------------------------------------------------------------------------------
 template <int S>
-NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2); }
+NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2) + 2 * S; }   // pairs + (av, aw) of precondition()
 
 template <int S>
 NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
@@ -569,6 +580,7 @@ struct Solver {
     I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
     I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
     sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+    I.sq *= P.inv_res; I.cq *= P.inv_res;
     I.bx = I.by = 0; I.fx = I.fy = 0.0f;
     if (P.cells != nullptr) {
       // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
@@ -596,6 +608,18 @@ struct Solver {
       for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
     }
     for (int e = 0; e < P.m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
+    {
+      float* tab = hist + (size_t)(P.m * PAIR) * stride;             // tracking-term majorants of precondition()
+      const float dt2 = 2.0f * P.dt * P.dt;
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) {
+        const int i = lg * S + j;
+        const int rem = P.N - i > 0 ? P.N - i : 1;                   // padded steps: any positive value
+        const float rowsum = (float)(rem * (i + 1) + ((rem - 1) * rem) / 2);
+        tab[(size_t)(2 * j) * stride] = dt2 * P.a_trans * rowsum;
+        tab[(size_t)(2 * j + 1) * stride] = dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N);
+      }
+    }
     f = 0.0f; pgmax = 0.0f; gamma = 1.0f;
     iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
     hist_len = 0; head = 0; small_steps = 0;
@@ -611,17 +635,16 @@ struct Solver {
   //   rowsum_i = (N-i)(i+1) + (N-i-1)(N-i)/2,  av = 2 (w_trans/N) dt^2 rowsum_i,
   //   aw = 2 (w_orient/N) dt^2 rowsum_i + 2 w_orient w_terminal dt^2 N.
   // The 3x3 block is inverted in closed form (Sherman-Morrison).  `on` = false leaves r unchanged (predicated).
-  NEOMPC_HD void precondition(const SolverConst& P, int lg, bool on, float (*r)[3]) const {
-    const float dt2 = 2.0f * P.dt * P.dt;
+  NEOMPC_HD void precondition(const SolverConst& P, const float* hist, int stride, bool on, float (*r)[3]) const {
+    const float* tab = hist + (size_t)(P.m * PAIR) * stride;         // (av_j, aw_j) written by init()
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      const int i = lg * S + j;
-      const float rowsum = (float)((P.N - i) * (i + 1) + ((P.N - i - 1) * (P.N - i)) / 2);
       const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
-      const float q = div_approx(1.0f, rx * rx + ry * ry + rz * rz + P.eps2);
-      const float k = P.w_ctrl * sqrtf(q);
-      const float iv = div_approx(1.0f, dt2 * P.a_trans * rowsum + k);
-      const float iw = div_approx(1.0f, dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N) + k);
+      const float ri = rsqrt_f(rx * rx + ry * ry + rz * rz + P.eps2);
+      const float q = ri * ri;
+      const float k = P.w_ctrl * ri;
+      const float iv = rcp_approx(tab[(size_t)(2 * j) * stride] + k);
+      const float iw = rcp_approx(tab[(size_t)(2 * j + 1) * stride] + k);
       const float tx = iv * rx, ty = iv * ry, tz = iw * rz;
       const float kq = k * q;
       const float den = 1.0f - kq * (rx * tx + ry * ty + rz * tz);
@@ -662,7 +685,7 @@ struct Solver {
     const bool use_pc = P.precond != 0 && !plain;
     const float h0 = P.precond ? 1.0f : (use_qn ? gamma : 1.0f);
     if (P.precond) {
-      precondition(P, lg, use_pc, r);
+      precondition(P, hist, stride, use_pc, r);
     } else {
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
@@ -842,6 +865,7 @@ struct Solver {
     const bool stateful = cr.stateful, new_goal = cr.new_goal;
     float ct, st;                                      // cos/sin of the true pose yaw (srv.py:317)
     sincos_f(rq.pose_yaw, &st, &ct);
+    st *= P.inv_res; ct *= P.inv_res;
     if (valid && plan != nullptr) {                   // the raw solution x.x (what publishLocalPlan gets, srv.py:365)
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) {
@@ -947,6 +971,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
   I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
   I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
   sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+  I.sq *= P.inv_res; I.cq *= P.inv_res;
   I.bx = I.by = 0; I.fx = I.fy = 0.0f;
   if (P.cells != nullptr) {
     const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
