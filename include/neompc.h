@@ -27,6 +27,18 @@ extern "C" {
 #define NEOMPC_MAX_FOOTPRINT_VERTICES 16
 #define NEOMPC_STATELESS 0xFFFFFFFFu  /* neompc_request.instance_id: cold start, no per-instance state */
 
+/* neompc_params.footprint_mode: how the footprint term of the objective (srv.py:238-244, 262-263) is evaluated.
+ * STATIC reproduces the reference: `update_footprint.points` aliases `self.footprint.points` (srv.py:227) and every
+ * vertex is restored right after it is written (:241-244), so the polygon tested at every step is the CURRENT footprint;
+ * the term is w_footprint when that polygon touches a lethal cell and 0 otherwise, independent of the controls.
+ * MOVING is what the loop at srv.py:238-244 sets out to do (it changes results, hence
+ * opt-in): the robot-frame polygon is placed at each predicted pose of the costmap rollout (srv.py:234-236) and
+ * rasterised there; every step whose polygon touches a lethal cell (or leaves the map) adds w_footprint / control_steps. */
+enum {
+  NEOMPC_FOOTPRINT_STATIC = 0,
+  NEOMPC_FOOTPRINT_MOVING = 1
+};
+
 /* error codes */
 enum {
   NEOMPC_OK = 0,
@@ -63,7 +75,8 @@ typedef struct neompc_params {
   int32_t lbfgs_memory;        /* history pairs, 1..8 (default 3) */
   float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254); default 1e-2 */
   int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
-  int32_t reserved[6];
+  int32_t footprint_mode;      /* NEOMPC_FOOTPRINT_* ; 0 = the reference's behaviour */
+  int32_t reserved[5];
 } neompc_params;
 
 /*
@@ -135,9 +148,9 @@ int neompc_set_params(neompc_handle* h, const neompc_params* params);
 int neompc_get_params(const neompc_handle* h, neompc_params* out);
 const char* neompc_last_error(const neompc_handle* h);   /* h may be NULL: last error of neompc_create on this thread */
 int neompc_version(void);
-/* sizeof() of the POD records as compiled, for binding self-checks: out[0..5] = request, response, params, optimizer_request,
- * robot_tick, carrot_info */
-int neompc_abi_sizes(size_t out[6]);
+/* sizeof() of the POD records as compiled, for binding self-checks: out[0..6] = request, response, params, optimizer_request,
+ * robot_tick, carrot_info, plan_pose */
+int neompc_abi_sizes(size_t out[7]);
 
 /* ---- environment ------------------------------------------------------------------------------------------ */
 /* Costmap2d(self) (srv.py:118).  cells: row-major uint8 [height][width], copied to the device (host pointer).
@@ -216,6 +229,23 @@ int neompc_build_requests(neompc_handle* h, const neompc_carrot_params* cp, cons
 int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* d_ticks,
                                  size_t n, uint32_t first_instance_id, neompc_request* d_reqs_out,
                                  neompc_carrot_info* d_info_out, void* stream);
+
+/* ---- the step after the solve: the predicted path -------------------------------- */
+/* One pose of the nav_msgs/Path the reference publishes on "/mpc_local_plan" (publishLocalPlan, srv.py:271-310):
+ * position x, y and the orientation quaternion_from_euler(0, 0, yaw) (srv.py:182-196; x = y = 0).  32 bytes. */
+typedef struct neompc_plan_pose {
+  double x, y;
+  double qz, qw;
+} neompc_plan_pose;
+/* publishLocalPlan(x.x) (srv.py:365) for n solved problems: plan = n * 3*control_steps floats (the plan output of
+ * neompc_solve_batch*), poses_out = n * (control_steps + 1) poses; pose 0 is the start pose (position only, identity
+ * orientation, srv.py:288-291).  The reference rolls from the TF pose map -> base_link (srv.py:274-286); here the
+ * request's current_pose is used (same thing when the costmap's global frame is "map").  Host buffers, synchronous. */
+int neompc_local_plan(neompc_handle* h, const neompc_request* reqs, const float* plan, size_t n,
+                      neompc_plan_pose* poses_out);
+/* Same on device buffers, asynchronous on `stream` (NULL = the handle's stream). */
+int neompc_local_plan_device(neompc_handle* h, const neompc_request* d_reqs, const float* d_plan, size_t n,
+                             neompc_plan_pose* d_poses_out, void* stream);
 
 /* ---- test hooks ------------------------------------------------------------------------------------------- */
 /* objective(cmd_vel) (srv.py:204-269) and its analytic gradient for n (request, u) pairs; host buffers.

@@ -15,6 +15,7 @@ EXPORTS = [
     "neompc_set_footprint", "neompc_reserve_instances", "neompc_reset_state", "neompc_get_state",
     "neompc_solve_batch", "neompc_solve_batch_device", "neompc_solve_msgs", "neompc_pack_requests",
     "neompc_set_plan", "neompc_build_requests", "neompc_build_requests_device",
+    "neompc_local_plan", "neompc_local_plan_device",
     "neompc_eval_objective", "neompc_launch_count", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
 ]
 
@@ -69,6 +70,8 @@ def load():
     lib.neompc_set_plan.argtypes = [vp, vp, sz]
     lib.neompc_build_requests.argtypes = [vp, vp, vp, sz, u32, vp, vp]
     lib.neompc_build_requests_device.argtypes = [vp, vp, vp, sz, u32, vp, vp, vp]
+    lib.neompc_local_plan.argtypes = [vp, vp, vp, sz, vp]
+    lib.neompc_local_plan_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.neompc_eval_objective.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.neompc_launch_count.argtypes = [vp]
     lib.neompc_launch_count.restype = ctypes.c_uint64

@@ -57,6 +57,10 @@ assert CARROT_INFO_DTYPE.itemsize == 16
 CARROT_PARAMS_DTYPE = np.dtype([("lookahead_dist_min", "<f4"), ("lookahead_dist_max", "<f4"),
                                 ("lookahead_dist_close_to_goal", "<f4"), ("controller_frequency", "<f4")])
 
+# neompc_plan_pose — one pose of the predicted path (publishLocalPlan, srv.py:271-310), 32 bytes
+PLAN_POSE_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("qz", "<f8"), ("qw", "<f8")])
+assert PLAN_POSE_DTYPE.itemsize == 32
+
 # neompc_response.status
 STATUS_CONVERGED = 0
 STATUS_MAXITER = 1
@@ -70,6 +74,10 @@ FLAG_STOPPED = 8              # zero twist returned (srv.py:374-377)
 
 ENC_OCCUPANCY = 0
 ENC_NAV2_RAW = 1
+
+# neompc_params.footprint_mode
+FOOTPRINT_STATIC = 0          # the reference: the polygon never moves (aliasing at srv.py:227,241-244)
+FOOTPRINT_MOVING = 1          # opt-in: polygon placed at every predicted pose
 
 # neompc_params — the reference's 22 server parameters (srv.py:49-75) + solver knobs
 PARAMS_FIELDS = [
@@ -86,7 +94,8 @@ PARAMS_FIELDS = [
     ("lbfgs_memory", "<i4"),
     ("control_smoothing", "<f4"),
     ("lanes_per_instance", "<i4"),
-    ("reserved", "<i4", (6,)),
+    ("footprint_mode", "<i4"),
+    ("reserved", "<i4", (5,)),
 ]
 PARAMS_DTYPE = np.dtype(PARAMS_FIELDS, align=False)
 assert PARAMS_DTYPE.itemsize == 128

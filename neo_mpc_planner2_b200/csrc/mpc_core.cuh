@@ -62,7 +62,10 @@ struct SolverConst {
   float w_ctrl;        // w_control / N                               (srv.py:253-254)
   float bt_term;       // w_orient * w_terminal                       (srv.py:268)
   float wt_term;       // w_trans * w_terminal
-  float w_fp;          // w_footprint: N * (1.0^2 * w_footprint / N)  (srv.py:263)
+  float w_fp;          // w_footprint: N * (1.0^2 * w_footprint / N)  (srv.py:263); 0 in the moving-footprint mode
+  float w_fp_step;     // moving-footprint mode (NEOMPC_FOOTPRINT_MOVING): w_footprint / N per lethal step, else 0
+  int fp_mode;         // neompc_params.footprint_mode
+  int lethal_byte;     // the cell byte whose cost is 1.0 in the current encoding (100 or 254)
   float eps2;          // control_smoothing^2
   float lo[3], hi[3];  // box (srv.py:127-129)
   float R;             // max_vel_trans (srv.py:158)
@@ -353,6 +356,68 @@ struct Forward {
     return inb ? cell : kCellOob;
   }
 
+  // Moving-footprint mode (NEOMPC_FOOTPRINT_MOVING): is the robot-frame polygon, placed at the
+  // predicted pose (base-frame offset (x, y), heading change with cos/sin (c, s)) of the costmap rollout
+  // (srv.py:234-236), in collision?  nav2 FootprintCollisionChecker::footprintCost == 1.0 restated: vertices -> cells,
+  // every edge incl. last -> first walked with nav2's LineIterator (incremental Bresenham, both ends included); a
+  // vertex outside the map counts as lethal.  Run by ONE lane for one of its steps: no collectives inside.
+  static NEOMPC_HD bool footprint_lethal_at(const SolverConst& P, const Instance& I, float x, float y, float c, float s) {
+    // heading of the pose = start yaw + z, by angle addition; I.cq / I.sq carry the factor 1/resolution (cells)
+    const float cw = I.cq * c - I.sq * s, sw = I.sq * c + I.cq * s;
+    const float ox = I.fx + (I.cq * x - I.sq * y), oy = I.fy + (I.sq * x + I.cq * y);
+    int lethal = 0;
+    int mx0 = 0, my0 = 0, mxf = 0, myf = 0;
+    for (int v = 0; v <= P.fp_n; ++v) {
+      int mx, my;
+      if (v < P.fp_n) {
+        const float gx = ox + (cw * P.fp_x[v] - sw * P.fp_y[v]);
+        const float gy = oy + (sw * P.fp_x[v] + cw * P.fp_y[v]);
+#if defined(__CUDA_ARCH__)
+        mx = I.bx + __float2int_rd(gx);
+        my = I.by + __float2int_rd(gy);
+#else
+        mx = I.bx + (int)floorf(gx);
+        my = I.by + (int)floorf(gy);
+#endif
+        if ((unsigned)mx >= (unsigned)P.W || (unsigned)my >= (unsigned)P.H) {   // vertex off the map: cost 1.0
+          lethal = 1;
+          mx = mx < 0 ? 0 : (mx >= P.W ? P.W - 1 : mx);                         // keep the walk inside the grid
+          my = my < 0 ? 0 : (my >= P.H ? P.H - 1 : my);
+        }
+        if (v == 0) { mxf = mx; myf = my; mx0 = mx; my0 = my; continue; }
+      } else {
+        mx = mxf; my = myf;                       // closing edge last -> first
+      }
+      // all vertices are inside the grid here, so every pixel of the edge is too: no per-pixel bounds test
+      const int ddx = mx - mx0, ddy = my - my0;
+      const int adx = ddx < 0 ? -ddx : ddx, ady = ddy < 0 ? -ddy : ddy;
+      const int sxs = ddx >= 0 ? 1 : -1, sys = ddy >= 0 ? 1 : -1;
+      const bool xmaj = adx >= ady;
+      const int den = xmaj ? adx : ady, numadd = xmaj ? ady : adx;
+      const int step_major = xmaj ? sxs : sys * P.W;          // index increments along / across the major axis
+      const int step_minor = xmaj ? sys * P.W : sxs;
+      int num = den >> 1;
+      int idx = my0 * P.W + mx0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+      for (int k = 0; k <= den; ++k) {
+#if defined(__CUDA_ARCH__)
+        const int cell = (int)__ldg(P.cells + idx);
+#else
+        const int cell = (int)P.cells[idx];
+#endif
+        lethal |= (cell == P.lethal_byte) ? 1 : 0;
+        num += numadd;
+        const bool wrap = num >= den;
+        num -= wrap ? den : 0;
+        idx += step_major + (wrap ? step_minor : 0);
+      }
+      mx0 = mx; my0 = my;
+    }
+    return lethal != 0;
+  }
+
   // Rolls the omni-drive model over the horizon (srv.py:230-232): z, cos/sin, per-step displacement, position.
   // u[j][0..2] = (vx, vy, omega) of step lg*S + j.
   NEOMPC_HD void rollout(const SolverConst& P, const float (*u)[3], int lg) {
@@ -386,6 +451,12 @@ struct Forward {
     for (int j = 0; j < S; ++j)                                                     // srv.py:246-247 via :234-236
       cell[j] = cell_of(P, I, I.cq, I.sq, x[j], y[j]);                              // (loads issued together)
     float J = 0.0f;
+    if (P.fp_mode == NEOMPC_FOOTPRINT_MOVING && P.cells != nullptr && P.fp_n > 0) {      // uniform branch
+      for (int j = 0; j < S; ++j) {
+        const bool hit = footprint_lethal_at(P, I, x[j], y[j], c[j], s[j]);
+        J += (hit && lg * S + j < P.N) ? P.w_fp_step : 0.0f;                        // srv.py:262-263 per step
+      }
+    }
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;

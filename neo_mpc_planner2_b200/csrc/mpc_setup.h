@@ -55,6 +55,10 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
   }
   if (p.lbfgs_memory < 0 || p.lbfgs_memory > kMaxMemory) { err = "lbfgs_memory must be 0..8"; return false; }
   if (p.max_iterations < 0) { err = "max_iterations must be >= 0"; return false; }
+  if (p.footprint_mode != NEOMPC_FOOTPRINT_STATIC && p.footprint_mode != NEOMPC_FOOTPRINT_MOVING) {
+    err = "footprint_mode must be NEOMPC_FOOTPRINT_STATIC or NEOMPC_FOOTPRINT_MOVING";
+    return false;
+  }
   if (!(p.opt_tolerance > 0.0f)) { err = "opt_tolerance must be > 0"; return false; }
   const int g = p.lanes_per_instance;
   if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) {
@@ -84,7 +88,10 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.w_ctrl = p.w_control / (float)N;
   c.bt_term = p.w_orient * p.w_terminal;
   c.wt_term = p.w_trans * p.w_terminal;
-  c.w_fp = p.w_footprint;
+  c.fp_mode = p.footprint_mode;
+  c.w_fp = p.footprint_mode == NEOMPC_FOOTPRINT_MOVING ? 0.0f : p.w_footprint;
+  c.w_fp_step = p.footprint_mode == NEOMPC_FOOTPRINT_MOVING ? p.w_footprint / (float)N : 0.0f;
+  c.lethal_byte = 100;                            // NEOMPC_ENC_OCCUPANCY; set_costmap updates it with the encoding
   const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f) : 1e-2f;
   c.eps2 = eps * eps;
   c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "carrot.cuh"
+#include "local_plan.cuh"
 #include "kernels.cuh"
 #include "mpc_setup.h"
 
@@ -102,6 +103,7 @@ void rebuild_const(neompc_handle* h) {
   h->c.fp_n = old.fp_n;
   std::memcpy(h->c.fp_x, old.fp_x, sizeof(old.fp_x));
   std::memcpy(h->c.fp_y, old.fp_y, sizeof(old.fp_y));
+  h->c.lethal_byte = h->encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
   h->c.state = h->d_state;
   h->c.state_rows = h->state_rows;
   choose_tiling(h->params.control_steps, h->params.lanes_per_instance, &h->G, &h->S);
@@ -214,7 +216,7 @@ extern "C" {
 
 int neompc_version(void) { return NEOMPC_VERSION; }
 
-int neompc_abi_sizes(size_t out[6]) {
+int neompc_abi_sizes(size_t out[7]) {
   if (!out) return NEOMPC_ERR_INVALID;
   out[0] = sizeof(neompc_request);
   out[1] = sizeof(neompc_response);
@@ -222,6 +224,7 @@ int neompc_abi_sizes(size_t out[6]) {
   out[3] = sizeof(neompc_optimizer_request);
   out[4] = sizeof(neompc_robot_tick);
   out[5] = sizeof(neompc_carrot_info);
+  out[6] = sizeof(neompc_plan_pose);
   return NEOMPC_OK;
 }
 
@@ -337,6 +340,7 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
   h->resolution = resolution;
   if (encoding != h->encoding) {
     h->encoding = encoding;
+    h->c.lethal_byte = encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
     return upload_tables(h);
   }
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -522,6 +526,45 @@ int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const fl
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d_u); cudaFree(d_J);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_objective");
+  return NEOMPC_OK;
+}
+
+int neompc_local_plan_device(neompc_handle* h, const neompc_request* d_reqs, const float* d_plan, size_t n,
+                             neompc_plan_pose* d_poses_out, void* stream) {
+  if (!h || (n > 0 && (!d_reqs || !d_plan || !d_poses_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  if (n > 0xffffffffu) return fail(h, NEOMPC_ERR_INVALID, "batch too large");
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  const int N = h->params.control_steps;
+  // self.dt = prediction_horizon / no_ctrl_steps (srv.py:137), in float64 like the reference
+  const double dt = (double)h->params.prediction_horizon / (double)N;
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  cudaError_t e = launch_local_plan(d_reqs, d_plan, (unsigned)n, N, dt, d_poses_out, s);
+  if (e != cudaSuccess) return cuda_fail(h, e, "local_plan kernel launch");
+  h->launches += 1;
+  return NEOMPC_OK;
+}
+
+int neompc_local_plan(neompc_handle* h, const neompc_request* reqs, const float* plan, size_t n,
+                      neompc_plan_pose* poses_out) {
+  if (!h || (n > 0 && (!reqs || !plan || !poses_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  const size_t N = (size_t)h->params.control_steps;
+  int rc = ensure_staging(h, n, true, false);
+  if (rc != NEOMPC_OK) return rc;
+  neompc_plan_pose* d_poses = nullptr;
+  NEOMPC_CUDA(h, cudaMalloc(&d_poses, n * (N + 1) * sizeof(neompc_plan_pose)));
+  cudaError_t e = cudaMemcpyAsync(h->d_reqs, reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_plan, plan, n * 3 * N * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    rc = neompc_local_plan_device(h, h->d_reqs, h->d_plan, n, d_poses, h->stream);
+    if (rc != NEOMPC_OK) { cudaFree(d_poses); return rc; }
+    e = cudaMemcpyAsync(poses_out, d_poses, n * (N + 1) * sizeof(neompc_plan_pose), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_poses);
+  if (e != cudaSuccess) return cuda_fail(h, e, "local_plan");
   return NEOMPC_OK;
 }
 

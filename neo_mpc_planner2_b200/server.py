@@ -72,6 +72,12 @@ class OptimizerResponse:
     output_vel: TwistStamped = field(default_factory=TwistStamped)
 
 
+@dataclass
+class Path:
+    frame_id: str = "map"                       # srv.py:309
+    poses: list = field(default_factory=list)   # PoseStamped
+
+
 def _pose7(pose):
     p, q = pose.position, pose.orientation
     return [p.x, p.y, p.z, q.x, q.y, q.z, q.w]
@@ -125,7 +131,9 @@ class MpcOptimizationServer:
         self._solver.reserve_instances(1)
         self.last_time = 0.0                      # srv.py:138
         self.last_response = None
-        self.local_plan = None                    # the solver's plan, what publishLocalPlan would publish (srv.py:365)
+        self.solution = None                      # x.x of srv.py:363: the solver's controls, 3*control_steps
+        self.local_plan = Path()                  # srv.py:109: what publishLocalPlan publishes on /mpc_local_plan
+        self.PubRaysPath = None                   # srv.py:107-108: any object with .publish(path); None = keep only
 
     # -- environment inputs (the reference gets these from ROS topics)
     def set_costmap(self, cells, resolution, origin_x, origin_y, encoding=ENC_OCCUPANCY):
@@ -154,8 +162,26 @@ class MpcOptimizationServer:
         response.output_vel.twist.linear.y = float(out["vy"][0])
         response.output_vel.twist.angular.z = float(out["omega"][0])
         self.last_response = out[0]
-        self.local_plan = plan[0]
+        self.solution = plan[0]
+        self.publishLocalPlan(plan[0], request.current_pose.pose)                # srv.py:365
         return response
+
+    def publishLocalPlan(self, x, start_pose=None):
+        """srv.py:271-310: roll the plan x from the robot pose and publish it as a Path.  The reference reads the pose
+        from TF (map -> base_link, srv.py:274-286); the mirror takes the request's current_pose.  The rollout itself
+        runs on the device (neompc_local_plan)."""
+        if start_pose is None:
+            return
+        q = start_pose.orientation
+        req = np.zeros(1, REQUEST_DTYPE)
+        req["pose_x"], req["pose_y"] = start_pose.position.x, start_pose.position.y
+        req["pose_yaw"] = math.atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z))   # srv.py:176-178
+        poses = self._solver.local_plan(req, np.asarray(x, np.float32)[None, :])[0]
+        self.local_plan = Path(poses=[
+            PoseStamped(pose=Pose(Vector3(float(p["x"]), float(p["y"]), 0.0),
+                                  Quaternion(0.0, 0.0, float(p["qz"]), float(p["qw"])))) for p in poses])
+        if self.PubRaysPath is not None:
+            self.PubRaysPath.publish(self.local_plan)
 
     def close(self):
         self._solver.close()

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from .abi import (REQUEST_DTYPE, RESPONSE_DTYPE, PARAMS_DTYPE, MSG_DTYPE, ENC_OCCUPANCY, params_record,
-                  TICK_DTYPE, CARROT_INFO_DTYPE, CARROT_PARAMS_DTYPE, STATELESS)
+                  TICK_DTYPE, CARROT_INFO_DTYPE, CARROT_PARAMS_DTYPE, PLAN_POSE_DTYPE, STATELESS)
 
 NeompcError = _lib.NeompcError
 
@@ -185,6 +185,23 @@ class BatchSolver:
             self._h, _ptr(carrot_params), ctypes.c_void_p(d_ticks), int(n), int(first_instance_id),
             ctypes.c_void_p(d_reqs), ctypes.c_void_p(d_info), ctypes.c_void_p(stream) if stream else None),
             "neompc_build_requests_device")
+
+    # ------------------------------------------------------------------ the step after: predicted path (srv.py:271-310)
+    def local_plan(self, reqs, plan):
+        """publishLocalPlan for n solved problems: [n, control_steps + 1] poses (x, y, qz, qw), host buffers."""
+        reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)
+        n = len(reqs)
+        plan = np.ascontiguousarray(plan, dtype=np.float32).reshape(n, 3 * self.control_steps)
+        poses = np.empty((n, self.control_steps + 1), PLAN_POSE_DTYPE)
+        self._check(self._lib.neompc_local_plan(self._h, _ptr(reqs), _ptr(plan), n, _ptr(poses)), "neompc_local_plan")
+        return poses
+
+    def local_plan_device(self, d_reqs, d_plan, n, d_poses, stream=None):
+        if stream == 0:
+            stream = 1
+        self._check(self._lib.neompc_local_plan_device(
+            self._h, ctypes.c_void_p(d_reqs), ctypes.c_void_p(d_plan), int(n), ctypes.c_void_p(d_poses),
+            ctypes.c_void_p(stream) if stream else None), "neompc_local_plan_device")
 
     def eval_objective(self, reqs, u, want_grad=True):
         reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)

@@ -22,5 +22,5 @@ from .costmap import GridCostmap, ENC_OCCUPANCY, ENC_NAV2_RAW  # noqa: F401
 from .mpc_oracle import (  # noqa: F401
     MpcParams, Problem, OracleServer, objective, f_constraint, euler_yaw, quirk_yaw,
     slsqp_solve, objective_batch, gradient_batch, collision_check, initial_guess_update,
-    quat_from_yaw,
+    quat_from_yaw, local_plan, footprint_at, moving_footprint_lethal,
 )

@@ -144,12 +144,17 @@ def quirk_yaw(pose_quat, goal_quat):
 # --------------------------------------------------------------------------------------
 # objective (srv.py:204-269) and constraint (srv.py:157-158): scalar, bit-exact restatement
 # --------------------------------------------------------------------------------------
-def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel):
+def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel, moving_footprint=None):
     """J(cmd_vel).  ``footprint_world`` is the polygon the reference holds in
     ``self.footprint`` (world-frame vertices, list of (x, y)); because of the aliasing at
     srv.py:227/241-244 it never moves, so its cost is the same at every step.
     ``prob`` supplies the hoisted yaws: carrot_yaw (srv.py:211), goal_yaw (:212),
-    pose_yaw_objective (:213, the goal-w quirk)."""
+    pose_yaw_objective (:213, the goal-w quirk).
+
+    ``moving_footprint`` (robot-frame vertices) selects the OPT-IN mode NEOMPC_FOOTPRINT_MOVING
+     — NOT the reference's behaviour: the polygon is placed at each predicted
+    pose (pos_x, pos_y, odom_yaw) of the costmap rollout (srv.py:234-236), which is what the loop at
+    srv.py:238-244 sets out to do, and tested there with the same ``== 1.0`` rule (srv.py:262-263)."""
     n_steps = params.control_steps
     dt = params.dt
     cost_total = 0
@@ -190,7 +195,9 @@ def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel):
         else:
             cost_total += params.w_costmap * costmap_cost / n_steps            # :260
 
-        if fp_cost is None:
+        if moving_footprint is not None:
+            fp_cost = costmap.getFootprintCost(_Poly(footprint_at(moving_footprint, pos_x, pos_y, odom_yaw)))
+        elif fp_cost is None:
             fp_cost = costmap.getFootprintCost(_Poly(footprint_world))
         if fp_cost == 1.0:                                                     # :262
             cost_total += (fp_cost ** 2) * params.w_footprint / n_steps        # :263
@@ -221,6 +228,13 @@ class _Poly:
         self.points = [p if hasattr(p, "x") else _Pt(p[0], p[1]) for p in (pts or [])]
 
 
+def footprint_at(footprint_robot, x, y, yaw):
+    """Robot-frame polygon placed at a predicted pose (moving-footprint mode; numpy float64 like the
+    rest of the objective)."""
+    c, s = np.cos(yaw), np.sin(yaw)
+    return [(x + (fx * c - fy * s), y + (fx * s + fy * c)) for fx, fy in footprint_robot]
+
+
 def footprint_world(footprint_robot, pose_x, pose_y, pose_yaw):
     """World-frame footprint polygon at the current pose — what nav2 publishes on
     ``/local_costmap/published_footprint`` and the reference stores at srv.py:154-155.
@@ -242,7 +256,7 @@ def make_bounds_and_constraints(params: MpcParams):
     return bnds, cons
 
 
-def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, maxiter=None):
+def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, maxiter=None, moving_footprint=None):
     """Exactly the reference's call (srv.py:363-364): SLSQP, finite-difference gradients."""
     if x0 is None:
         x0 = np.zeros(params.control_steps * 3)                                # srv.py:136
@@ -250,7 +264,7 @@ def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, 
     opts = {"ftol": params.opt_tolerance if ftol is None else ftol, "disp": False}
     if maxiter is not None:
         opts["maxiter"] = maxiter
-    fun = partial(objective, params, costmap, fp_world, prob)
+    fun = partial(objective, params, costmap, fp_world, prob, moving_footprint=moving_footprint)
     return minimize(fun, np.array(x0, dtype=np.float64), method="SLSQP",
                     bounds=bnds, constraints=cons, options=opts)
 
@@ -286,6 +300,22 @@ def collision_check(params: MpcParams, costmap, fp_world, prob, x):
             break
     fp_hit = costmap.getFootprintCost(_Poly(fp_world)) == 1.0                  # :343
     return hit, fp_hit
+
+
+def local_plan(params: MpcParams, pose_x, pose_y, pose_yaw, x):
+    """``publishLocalPlan(x)`` (srv.py:271-310): the poses of the published Path as rows
+    (x, y, qz, qw) — N + 1 of them; row 0 is the start pose (position only, default orientation,
+    srv.py:288-291).  (pose_x, pose_y, pose_yaw) stand for the TF lookup map -> base_link (:274-286)."""
+    dt = params.dt
+    pos_x, pos_y, yaw = pose_x, pose_y, pose_yaw
+    rows = [(pos_x, pos_y, 0.0, 1.0)]
+    for i in range(params.control_steps):                                     # :293
+        yaw += x[2 + 3 * i] * dt                                               # :295
+        pos_x += x[3 * i] * np.cos(yaw) * dt - x[1 + 3 * i] * np.sin(yaw) * dt  # :296
+        pos_y += x[3 * i] * np.sin(yaw) * dt + x[1 + 3 * i] * np.cos(yaw) * dt  # :297
+        q = quat_from_yaw(yaw)                                                 # :301 (x, y, z, w)
+        rows.append((pos_x, pos_y, q[2], q[3]))
+    return np.array(rows, dtype=np.float64)
 
 
 class OracleServer:
@@ -379,9 +409,24 @@ def rollout_batch(params: MpcParams, reqs, U, yaw_field="pose_yaw_objective"):
     return x, y, z, px, py
 
 
-def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None):
+def moving_footprint_lethal(params: MpcParams, costmap, reqs, U, footprint_robot):
+    """bool[B, N]: footprint at the predicted pose of step i in collision (moving-footprint mode)."""
+    n = params.control_steps
+    U = np.asarray(U, dtype=np.float64).reshape(len(U), n, 3)
+    _, _, z, px, py = rollout_batch(params, reqs, U)
+    yaw = _col(reqs, "pose_yaw_objective")[:, None] + z
+    out = np.zeros((len(U), n), dtype=bool)
+    for b in range(len(U)):
+        for i in range(n):
+            out[b, i] = costmap.getFootprintCost(_Poly(footprint_at(footprint_robot, px[b, i], py[b, i],
+                                                                   yaw[b, i]))) == 1.0
+    return out
+
+
+def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None, moving_footprint=None):
     """Vectorised J for a batch (same formula as ``objective``).  ``fp_lethal``: bool[B], whether
-    the current footprint cost == 1.0 (None -> all False).  ``costmap`` may be None (free space)."""
+    the current footprint cost == 1.0 (None -> all False).  ``costmap`` may be None (free space).
+    ``moving_footprint``: robot-frame polygon -> the opt-in moving-footprint mode (then fp_lethal is ignored)."""
     p = params
     n = p.control_steps
     U = np.asarray(U, dtype=np.float64).reshape(len(U), n, 3)
@@ -395,7 +440,9 @@ def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None):
     if costmap is not None:
         c = costmap.cost_at_world(px, py)
         J += (np.where(c == 1.0, 1000.0, p.w_costmap) * c ** 2 / n).sum(axis=1)
-    if fp_lethal is not None:
+    if moving_footprint is not None and costmap is not None:
+        J += moving_footprint_lethal(p, costmap, reqs, U, moving_footprint).sum(axis=1) * (p.w_footprint / n)
+    elif fp_lethal is not None:
         J += np.where(np.asarray(fp_lethal, dtype=bool), 1.0 * p.w_footprint, 0.0)
     dg2 = (_col(reqs, "carrot_x") - _col(reqs, "goal_x")) ** 2 + (_col(reqs, "carrot_y") - _col(reqs, "goal_y")) ** 2
     fe = _col(reqs, "goal_yaw") - z[:, -1]

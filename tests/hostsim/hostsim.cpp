@@ -28,6 +28,7 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.T.cost = e.tab.cost.data();
   e.T.flag = e.tab.flag.data();
   e.c.cells = cells;
+  e.c.lethal_byte = enc == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
   e.c.W = W; e.c.H = H;
   e.c.inv_res = (float)(1.0 / res);
   e.c.inv_res_d = 1.0 / res;

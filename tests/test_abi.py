@@ -27,11 +27,12 @@ def test_header_symbols_exported(lib):
 
 
 def test_record_sizes(lib):
-    sz = (ctypes.c_size_t * 6)()
+    sz = (ctypes.c_size_t * 7)()
     assert lib.neompc_abi_sizes(sz) == 0
     assert list(sz) == [abi.REQUEST_DTYPE.itemsize, abi.RESPONSE_DTYPE.itemsize, abi.PARAMS_DTYPE.itemsize,
-                        abi.MSG_DTYPE.itemsize, abi.TICK_DTYPE.itemsize, abi.CARROT_INFO_DTYPE.itemsize] \
-        == [64, 32, 128, 240, 48, 16]
+                        abi.MSG_DTYPE.itemsize, abi.TICK_DTYPE.itemsize, abi.CARROT_INFO_DTYPE.itemsize,
+                        abi.PLAN_POSE_DTYPE.itemsize] \
+        == [64, 32, 128, 240, 48, 16, 32]
     assert lib.neompc_version() == 100
 
 
