@@ -1,5 +1,6 @@
 // kernels.cuh — __global__ wrappers around the lane-group solver core (mpc_core.cuh) and their launchers.
-// One translation unit per lanes-per-instance value G (solve_g1.cu ... solve_g32.cu) instantiates S = 1..6.
+// One translation unit per lanes-per-instance value G (solve_g1.cu ... solve_g32.cu; G = 1,2,3,4,5,6,8,10,16,32)
+// instantiates S = 1..6.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -28,8 +29,22 @@ struct LaunchArgs {
   float* J;                    // device [n]
   float* grad;                 // device [n*3N] or null
   cudaStream_t stream;
-  unsigned* queue_counter;     // device word for the persistent kernel's work queue; null = one instance per group
-  int sm_count;
+};
+
+// thread -> (instance slot of the block, lane inside the group): 32/G groups per warp, leftover lanes idle
+template <int G>
+struct GroupMap {
+  static constexpr int kPerWarp = 32 / G;
+  static constexpr int kPerBlock = kPerWarp * (kBlockThreads / 32);
+  int slot, lg;
+  bool lane_ok;
+  __device__ __forceinline__ GroupMap() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G;
+    lg = lane - grp * G;
+    lane_ok = grp < kPerWarp;
+    slot = warp * kPerWarp + (lane_ok ? grp : kPerWarp - 1);
+  }
 };
 
 // cost tables staged once per block in shared memory
@@ -64,9 +79,12 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 #ifndef NEOMPC_MINBLOCKS_S3
 #define NEOMPC_MINBLOCKS_S3 4
 #endif
+#ifndef NEOMPC_MINBLOCKS_S2
+#define NEOMPC_MINBLOCKS_S2 5
+#endif
 // resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
 constexpr int min_blocks_for(int S) {
-  return (S == 2 ? 5 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2) * (128 / kBlockThreads);
+  return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2) * (128 / kBlockThreads);
 }
 
 // ---- TMA (bulk async copy) staging of the block's request tile ------------------------------------------------
@@ -110,100 +128,30 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   __shared__ SmemTables st;
   load_tables(st, lut_cost, lut_flag);
   CostTables T{st.cost, st.flag};
-  constexpr int kInstPerBlock = kBlockThreads / G;
+  constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   __shared__ alignas(128) neompc_request s_req[kInstPerBlock];
   __shared__ alignas(8) unsigned long long s_mbar;
   const unsigned first = blockIdx.x * kInstPerBlock;
   const unsigned in_block = n - first < (unsigned)kInstPerBlock ? n - first : (unsigned)kInstPerBlock;
   tma_stage_requests(s_req, &s_mbar, reqs + first, in_block);
-  const unsigned inst = first + threadIdx.x / G;
-  const int lg = threadIdx.x % G;
-  const bool valid = inst < n;
   // The record stays in shared memory: the solver core reads fields from there when it needs them (prologue and
   // epilogue) instead of holding 16 registers for the whole solve.  Slots past the end of the batch are zeroed.
   if (in_block < (unsigned)kInstPerBlock) {
-    if (!valid && lg == 0) {
-      float4* dst = reinterpret_cast<float4*>(&s_req[threadIdx.x / G]);
+    for (unsigned sl = in_block + threadIdx.x; sl < (unsigned)kInstPerBlock; sl += blockDim.x) {
+      float4* dst = reinterpret_cast<float4*>(&s_req[sl]);
       dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-      s_req[threadIdx.x / G].instance_id = NEOMPC_STATELESS;
+      s_req[sl].instance_id = NEOMPC_STATELESS;
     }
     __syncthreads();
   }
-  const neompc_request& rq = s_req[threadIdx.x / G];
-  solve_instance<G, S>(P, T, rq, valid, lg, hist_smem + threadIdx.x, kBlockThreads,
+  const GroupMap<G> gm;
+  const unsigned inst = first + gm.slot;
+  const bool valid = gm.lane_ok && inst < n;
+  const neompc_request& rq = s_req[gm.slot];
+  solve_instance<G, S>(P, T, rq, valid, gm.lg, hist_smem + threadIdx.x, kBlockThreads,
                        valid ? out + inst : nullptr,
                        (valid && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,
                        (valid && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
-}
-
-// Persistent variant: every lane group keeps pulling instances from a global counter until the batch is exhausted,
-// so a group that converges early does not idle while the slowest instance of its warp finishes (lock-step
-// efficiency of the one-instance-per-group kernel is ~0.6 at 8 instances per warp, profiles/lockstep_r1.txt).
-// The arithmetic of an instance does not depend on which group runs it or on its neighbours: results are
-// bit-identical to solve_kernel's.
-template <int G, int S>
-__global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
-solve_queue_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
-                   const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
-                   neompc_response* __restrict__ out, float* __restrict__ twist, float* __restrict__ plan,
-                   unsigned* __restrict__ counter) {
-  extern __shared__ float hist_smem[];
-  __shared__ SmemTables st;
-  load_tables(st, lut_cost, lut_flag);
-  CostTables T{st.cost, st.flag};
-  constexpr int kGroupsPerBlock = kBlockThreads / G;
-  const int lg = threadIdx.x % G;
-  const unsigned lane = threadIdx.x & 31u;
-  float* hist = hist_smem + threadIdx.x;
-  const unsigned total_groups = gridDim.x * kGroupsPerBlock;
-
-  Solver<G, S> sv;
-  // a defined, inert state for groups that have not been given an instance yet
-  sv.prologue(P, T, load_request(reqs, 0, false), false, lg, hist, kBlockThreads);
-  unsigned inst = 0;
-  bool need = true, exhausted = false, first_round = true;
-
-  constexpr int kGroupsPerWarp = 32 / G;
-  constexpr int kRefillAt = kGroupsPerWarp >= 4 ? kGroupsPerWarp / 2 : 1;   // refill once this many groups idle
-  while (true) {
-    const int idle = __popc(__ballot_sync(kFullMask, need && lg == 0));
-    const bool any_active = __any_sync(kFullMask, sv.active);
-    if (idle >= kRefillAt || (idle > 0 && !any_active)) {
-      // 1. finish the instances of the groups that just converged
-      const bool fin = need && sv.has_instance;
-      {
-        const neompc_request rq_done = load_request(reqs, inst, fin);
-        sv.epilogue(P, T, rq_done, fin, lg, fin ? out + inst : nullptr,
-                    (fin && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,
-                    (fin && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
-      }
-      // 2. next instance for every needy group: first round static, then one aggregated atomic per warp
-      unsigned nxt;
-      if (first_round) {
-        nxt = blockIdx.x * kGroupsPerBlock + threadIdx.x / G;
-      } else {
-        const unsigned want = __ballot_sync(kFullMask, need && lg == 0);
-        unsigned base = 0;
-        if (lane == 0 && want != 0) base = atomicAdd(counter, (unsigned)__popc(want));
-        base = __shfl_sync(kFullMask, base, 0);
-        nxt = total_groups + base + (unsigned)__popc(want & ((1u << lane) - 1u));
-        nxt = __shfl_sync(kFullMask, nxt, 0, G);          // lane 0 of each group holds the group's ticket
-      }
-      first_round = false;
-      const bool got = need && nxt < n;
-      const neompc_request rq = load_request(reqs, nxt, got);
-      const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
-      if (need) {
-        sv.init(P, rq, fp_any, got, lg, hist, kBlockThreads);
-        inst = nxt;
-        exhausted = !got;
-      }
-      need = false;
-    }
-    if (!__any_sync(kFullMask, sv.active)) break;
-    sv.pass(P, T, hist, kBlockThreads, lg);
-    need = need || (!sv.active && !exhausted);
-  }
 }
 
 template <int G, int S>
@@ -214,10 +162,11 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
   __shared__ SmemTables st;
   load_tables(st, lut_cost, lut_flag);
   CostTables T{st.cost, st.flag};
-  constexpr int kInstPerBlock = kBlockThreads / G;
-  const unsigned inst = blockIdx.x * kInstPerBlock + threadIdx.x / G;
-  const int lg = threadIdx.x % G;
-  const bool valid = inst < n;
+  constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
+  const GroupMap<G> gm;
+  const unsigned inst = blockIdx.x * kInstPerBlock + gm.slot;
+  const int lg = gm.lg;
+  const bool valid = gm.lane_ok && inst < n;
   const neompc_request rq = load_request(reqs, inst, valid);
   eval_instance<G, S>(P, T, rq, valid, lg, valid ? u + (size_t)inst * 3 * P.N : nullptr,
                       valid ? J + inst : nullptr,
@@ -227,24 +176,8 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
 template <int G, int S>
 cudaError_t launch_solve_gs(const LaunchArgs& a) {
   const size_t smem = (size_t)kBlockThreads * hist_floats_per_lane<S>(a.P.m) * sizeof(float);
-  constexpr int kInstPerBlock = kBlockThreads / G;
+  constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const unsigned blocks_needed = (a.n + kInstPerBlock - 1) / kInstPerBlock;
-  if (a.queue_counter != nullptr) {
-    // persistent launch: as many blocks as fit on the device at once; the rest of the batch is pulled from the queue
-    cudaError_t e = cudaFuncSetAttribute(solve_queue_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_queue_kernel<G, S>, kBlockThreads, smem);
-    if (e != cudaSuccess) return e;
-    const unsigned resident = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)a.sm_count;
-    if (blocks_needed > resident) {
-      e = cudaMemsetAsync(a.queue_counter, 0, sizeof(unsigned), a.stream);
-      if (e != cudaSuccess) return e;
-      solve_queue_kernel<G, S><<<resident, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n,
-                                                                            a.out, a.twist, a.plan, a.queue_counter);
-      return cudaGetLastError();
-    }
-  }
   cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   solve_kernel<G, S><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
@@ -254,7 +187,7 @@ cudaError_t launch_solve_gs(const LaunchArgs& a) {
 
 template <int G, int S>
 cudaError_t launch_eval_gs(const LaunchArgs& a) {
-  constexpr int kInstPerBlock = kBlockThreads / G;
+  constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const unsigned grid = (a.n + kInstPerBlock - 1) / kInstPerBlock;
   eval_kernel<G, S><<<grid, kBlockThreads, 0, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.u, a.J, a.grad);
   return cudaGetLastError();
@@ -276,8 +209,12 @@ cudaError_t launch_for_g(bool eval, int S, const LaunchArgs& a) {
 // defined in solve_g*.cu
 cudaError_t launch_g1(bool eval, int S, const LaunchArgs& a);
 cudaError_t launch_g2(bool eval, int S, const LaunchArgs& a);
+cudaError_t launch_g3(bool eval, int S, const LaunchArgs& a);
 cudaError_t launch_g4(bool eval, int S, const LaunchArgs& a);
+cudaError_t launch_g5(bool eval, int S, const LaunchArgs& a);
+cudaError_t launch_g6(bool eval, int S, const LaunchArgs& a);
 cudaError_t launch_g8(bool eval, int S, const LaunchArgs& a);
+cudaError_t launch_g10(bool eval, int S, const LaunchArgs& a);
 cudaError_t launch_g16(bool eval, int S, const LaunchArgs& a);
 cudaError_t launch_g32(bool eval, int S, const LaunchArgs& a);
 

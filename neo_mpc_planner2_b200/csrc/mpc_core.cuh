@@ -104,43 +104,64 @@ NEOMPC_HD int state_stride_for(int n_steps) { return 3 * n_steps + kStateExtra; 
 // ---------------------------------------------------------------------------------------------------------
 // lane-group collectives
 // ---------------------------------------------------------------------------------------------------------
+// G lanes of one warp form a group, 32/G groups per warp (lanes past the last full group idle when G does not
+// divide 32, e.g. G = 5: six groups, lanes 30-31 unused).  Powers of two use butterfly exchanges; other sizes run a
+// Hillis-Steele scan inside the group and broadcast the total from its last lane.  Either way every lane of a group
+// ends up with bit-identical scalars, so the lanes of a group always take the same decisions.
 template <int G>
 struct Grp {
-  static NEOMPC_HD float sum(float v) {
+  static constexpr bool kPow2 = (G & (G - 1)) == 0;
+  static constexpr int kPerWarp = 32 / G;          // groups (= instances) per warp
 #if defined(__CUDA_ARCH__)
-    NEOMPC_UNROLL
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  static __device__ __forceinline__ int lane() { return (int)(threadIdx.x & 31u); }
 #endif
-    return v;
-  }
-  static NEOMPC_HD float max(float v) {
+  template <class Op>
+  static NEOMPC_HD float reduce(float v, Op op) {
 #if defined(__CUDA_ARCH__)
-    NEOMPC_UNROLL
-    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
-#endif
-    return v;
-  }
-  static NEOMPC_HD int imax(int v) {
-#if defined(__CUDA_ARCH__)
-    NEOMPC_UNROLL
-    for (int o = G / 2; o > 0; o >>= 1) {
-      int t = __shfl_xor_sync(kFullMask, v, o);
-      v = t > v ? t : v;
+    if (kPow2) {
+      NEOMPC_UNROLL
+      for (int o = G / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFullMask, v, o));
+    } else {
+      const int ln = lane(), lg = ln % G;
+      NEOMPC_UNROLL
+      for (int o = 1; o < G; o <<= 1) {
+        const float t = __shfl_sync(kFullMask, v, ln - o);
+        if (lg >= o) v = op(v, t);
+      }
+      v = __shfl_sync(kFullMask, v, ln - lg + (G - 1));
     }
+#else
+    (void)op;
 #endif
+    return v;
+  }
+  struct Add { NEOMPC_HD float operator()(float a, float b) const { return a + b; } };
+  struct Max { NEOMPC_HD float operator()(float a, float b) const { return fmaxf(a, b); } };
+  static NEOMPC_HD float sum(float v) { return reduce(v, Add()); }
+  static NEOMPC_HD float max(float v) { return reduce(v, Max()); }
+  static NEOMPC_HD int imax(int v) {       // small non-negative flags/counters: exact in float
+    return (int)reduce((float)v, Max());
+  }
+  // the value lane 0 of the group holds
+  static NEOMPC_HD float bcast0(float v, int lg) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) return kPow2 ? __shfl_sync(kFullMask, v, 0, G) : __shfl_sync(kFullMask, v, lane() - lg);
+#endif
+    (void)lg;
     return v;
   }
   // sum of v over the lanes of the group that come BEFORE this lane
   static NEOMPC_HD float excl_prefix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
     if (G > 1) {
+      const int ln = lane();
       float incl = v;
       NEOMPC_UNROLL
       for (int o = 1; o < G; o <<= 1) {
-        float t = __shfl_up_sync(kFullMask, incl, o, G);
+        const float t = kPow2 ? __shfl_up_sync(kFullMask, incl, o, G) : __shfl_sync(kFullMask, incl, ln - o);
         if (lg >= o) incl += t;
       }
-      float ex = __shfl_up_sync(kFullMask, incl, 1, G);
+      const float ex = kPow2 ? __shfl_up_sync(kFullMask, incl, 1, G) : __shfl_sync(kFullMask, incl, ln - 1);
       return lg > 0 ? ex : 0.0f;
     }
 #endif
@@ -151,13 +172,14 @@ struct Grp {
   static NEOMPC_HD float excl_suffix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
     if (G > 1) {
+      const int ln = lane();
       float incl = v;
       NEOMPC_UNROLL
       for (int o = 1; o < G; o <<= 1) {
-        float t = __shfl_down_sync(kFullMask, incl, o, G);
+        const float t = kPow2 ? __shfl_down_sync(kFullMask, incl, o, G) : __shfl_sync(kFullMask, incl, ln + o);
         if (lg + o < G) incl += t;
       }
-      float ex = __shfl_down_sync(kFullMask, incl, 1, G);
+      const float ex = kPow2 ? __shfl_down_sync(kFullMask, incl, 1, G) : __shfl_sync(kFullMask, incl, ln + 1);
       return lg + 1 < G ? ex : 0.0f;
     }
 #endif
@@ -965,13 +987,9 @@ struct Solver {
     bool collision = cr.latched || hit != 0;
     float wait = cr.waiting;
     float o[3];
-#if defined(__CUDA_ARCH__)
-    o[0] = __shfl_sync(kFullMask, ue[0][0], 0, G);
-    o[1] = __shfl_sync(kFullMask, ue[0][1], 0, G);
-    o[2] = __shfl_sync(kFullMask, ue[0][2], 0, G);
-#else
-    o[0] = ue[0][0]; o[1] = ue[0][1]; o[2] = ue[0][2];
-#endif
+    o[0] = Grp<G>::bcast0(ue[0][0], lg);
+    o[1] = Grp<G>::bcast0(ue[0][1], lg);
+    o[2] = Grp<G>::bcast0(ue[0][2], lg);
     unsigned flags = 0;
     if (collision || fp_hit) {                                                          // srv.py:374-382
       o[0] = o[1] = o[2] = 0.0f;

@@ -61,8 +61,8 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
   }
   if (!(p.opt_tolerance > 0.0f)) { err = "opt_tolerance must be > 0"; return false; }
   const int g = p.lanes_per_instance;
-  if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) {
-    err = "lanes_per_instance must be 0 (auto) or a power of two <= 32";
+  if (!(g == 0 || g == 1 || g == 2 || g == 3 || g == 4 || g == 5 || g == 6 || g == 8 || g == 10 || g == 16 || g == 32)) {
+    err = "lanes_per_instance must be 0 (auto) or one of 1, 2, 3, 4, 5, 6, 8, 10, 16, 32";
     return false;
   }
   return true;
@@ -113,16 +113,41 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.state_rows = 0;
 }
 
-// lanes-per-instance G and steps-per-lane S for a horizon of n steps (G*S >= n, S <= 6)
+// lanes-per-instance G and steps-per-lane S for a horizon of n steps (G*S >= n, S <= 6).
+// Auto mode minimises a cost model fitted to sweeps on B200 (profiles/tiling_sweep_r1b.txt, tiling_sweep_r1c.txt):
+//   time per instance  ~  c(S) * shuffles(G) * lockstep(32/G) / (32/G)
+// c(S): warp instructions of one solver pass with S steps per lane (S >= 5 spills registers); shuffles(G): scans and
+// reductions take ceil(log2 G) exchange steps, and a group size that is not a power of two pays ~20 % on top (scan +
+// broadcast instead of butterflies, computed source lanes); lockstep: the groups of a warp wait for the slowest one,
+// which costs more the more groups there are.  Measured: N=10 (4,3) 0.458 ms = (5,2) 0.459 ms, (8,2) 0.537;
+// N=20 (8,3) 1.66 ms, (10,2) 1.73, (16,2) 2.04, (5,4) 2.09; N=3 (1,3) 0.168 ms, (2,2) 0.182, (3,1) 0.200.
+constexpr int kGroupSizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 16, 32};
+inline double tiling_cost(int g, int s) {
+  static const double c[7] = {0.0, 0.35, 0.62, 1.0, 1.55, 2.9, 3.8};
+  int lg2 = 0;
+  while ((1 << lg2) < g) ++lg2;
+  const bool pow2 = (g & (g - 1)) == 0;
+  const int per_warp = 32 / g;
+  const double shuffles = (1.0 + 0.04 * lg2) * (pow2 ? 1.0 : 1.2);
+  const double lockstep = 1.0 + 0.05 * std::log2((double)per_warp);
+  return c[s] * shuffles * lockstep / per_warp;
+}
+
 inline void choose_tiling(int n_steps, int lanes_override, int* G, int* S) {
   int g = lanes_override;
   if (g <= 0) {
-    // measured on B200 (profiles/tiling_sweep_r1.txt): 3 steps per lane is fastest for N = 10 and 20, 2 for N = 3
-    const int target = n_steps <= 4 ? 2 : 3;
-    g = 1;
-    while ((n_steps + g - 1) / g > target && g < 32) g <<= 1;
+    double best = 1e300;
+    for (int cand : kGroupSizes) {
+      const int s = (n_steps + cand - 1) / cand;
+      if (s > 6) continue;
+      const double t = tiling_cost(cand, s);
+      if (t < best) { best = t; g = cand; }
+    }
+  } else {
+    // a requested group size that would need more than 6 steps per lane: next larger size that fits
+    for (int cand : kGroupSizes)
+      if (cand >= g && (n_steps + cand - 1) / cand <= 6) { g = cand; break; }
   }
-  while ((n_steps + g - 1) / g > 6 && g < 32) g <<= 1;         // S is instantiated up to 6
   *G = g;
   *S = (n_steps + g - 1) / g;
 }

@@ -48,9 +48,7 @@ struct neompc_handle {
   neompc_robot_tick* d_ticks = nullptr;
   neompc_carrot_info* d_info = nullptr;
   size_t cap_ticks = 0;
-  unsigned* d_queue = nullptr;     // work-queue counter of the persistent solve kernel
   int sm_count = 0;
-  bool use_queue = false;
   std::string err;
 };
 
@@ -138,8 +136,12 @@ cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   switch (h->G) {
     case 1: return launch_g1(eval, h->S, a);
     case 2: return launch_g2(eval, h->S, a);
+    case 3: return launch_g3(eval, h->S, a);
     case 4: return launch_g4(eval, h->S, a);
+    case 5: return launch_g5(eval, h->S, a);
+    case 6: return launch_g6(eval, h->S, a);
     case 8: return launch_g8(eval, h->S, a);
+    case 10: return launch_g10(eval, h->S, a);
     case 16: return launch_g16(eval, h->S, a);
     case 32: return launch_g32(eval, h->S, a);
     default: return cudaErrorInvalidValue;
@@ -202,8 +204,6 @@ int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, ne
   a.twist = d_twist;
   a.plan = d_plan;
   a.stream = s;
-  a.queue_counter = h->use_queue ? h->d_queue : nullptr;
-  a.sm_count = h->sm_count;
   cudaError_t e = dispatch(h, false, a);
   if (e != cudaSuccess) return cuda_fail(h, e, "solve kernel launch");
   h->launches += 1;
@@ -258,10 +258,8 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-  CREATE_CUDA(cudaMalloc(&h->d_queue, sizeof(unsigned)));
   CREATE_CUDA(cudaMalloc(&h->d_raw_table, 256));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
-  h->use_queue = std::getenv("NEOMPC_USE_QUEUE") != nullptr;   // opt-in: measured slower (profiles/queue_vs_plain_r1.txt)
   CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_lut_flag, kTableSize + 6));
 #undef CREATE_CUDA
@@ -279,7 +277,7 @@ int neompc_destroy(neompc_handle* h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
-  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs); cudaFree(h->d_queue);
+  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
   delete h;
   return NEOMPC_OK;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU box: kernel time per (config, lanes-per-instance) at large batch
-for spec in "c2 65536 1" "c2 65536 2" "c2 65536 4" "c3 65536 2" "c3 65536 4" "c3 65536 8" "c3 65536 16" "c4 131072 4" "c4 131072 8" "c4 131072 16" "c4 131072 32"; do
+for spec in "c2 65536 1" "c2 65536 2" "c2 65536 3" "c3 65536 3" "c3 65536 4" "c3 65536 5" "c3 65536 6" "c3 65536 8" "c3 65536 10" "c4 131072 5" "c4 131072 6" "c4 131072 8" "c4 131072 10" "c4 131072 16"; do
   set -- $spec
   timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --config $1 --batch $2 --lanes $3 2>&1 | python -c "
 import sys,json
