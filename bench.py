@@ -198,7 +198,7 @@ def run_ours(args):
     wl = workloads.config(args.config, batch=per_gpu, seed=None if rank == 0 else 1000 + rank)
     n = wl.batch
     n_steps = wl.control_steps
-    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes)
+    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode)
     solver.load_workload(wl)
     G, S = solver.tiling
 
@@ -302,6 +302,7 @@ def run_ours(args):
                        "steps_per_lane": S, "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
                        "parallelism": f"batch sharded over {world} GPU(s), one NCCL all-gather of (vx,vy,omega)"
                        if world > 1 else "single GPU", "cold_start": True,
+                       "footprint_mode": "moving (opt-in, not the reference's objective)" if args.footprint_mode else "static (reference)",
                        "iters_median": iters_med, "evals_mean": evals_mean},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
@@ -313,7 +314,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.footprint_mode:
             # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)
             import subprocess
             sample = args.cpu_sample or {"c2": 2048, "c3": 256, "c4": 64, "c5": 256}[args.config]   # ~15 core-seconds
@@ -322,7 +323,7 @@ def run_ours(args):
             dump = os.path.join(tempfile.mkdtemp(prefix="neompc_ref_"), "ref.npz")
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config",
                                   args.config, "--steps", "2", "--warmup", "1", "--cpu-sample", str(sample),
-                                  "--batch", str(n), "--dump-ref", dump],
+                                  "--batch", str(per_gpu), "--dump-ref", dump],
                                  capture_output=True, text=True, env=env, timeout=600)
             try:
                 ref = json.loads(res.stdout.strip().splitlines()[-1])
@@ -369,6 +370,9 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per instance (0 = auto)")
+    ap.add_argument("--footprint-mode", type=int, default=0, choices=[0, 1],
+                    help="0 = the reference's static footprint term (default, parity mode); 1 = opt-in moving footprint "
+                         "(SURVEY 8f row N1; no CPU baseline / cost residual for it)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ref", default="", help="reference arm: save per-problem J and x of the last pass (npz)")
