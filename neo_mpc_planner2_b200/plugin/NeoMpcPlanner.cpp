@@ -155,6 +155,18 @@ geometry_msgs::msg::TwistStamped NeoMpcPlanner::computeVelocityCommands(
   if (neompc_solve_msgs(mpc_, &m, 1, &last_response_, last_plan_.data()) != NEOMPC_OK)
     throw nav2_core::ControllerException(std::string("neompc_solve_msgs failed: ") + neompc_last_error(mpc_));
 
+  // the predicted path the Python server published on /mpc_local_plan (publishLocalPlan, srv.py:271-310, called :365)
+  {
+    neompc_request rq{};
+    rq.pose_x = (float)position.pose.position.x;
+    rq.pose_y = (float)position.pose.position.y;
+    const auto & q = position.pose.orientation;
+    rq.pose_yaw = (float)std::atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));   // srv.py:176-178
+    last_local_plan_.resize((size_t)params_.control_steps + 1);
+    if (neompc_local_plan(mpc_, &rq, last_plan_.data(), 1, last_local_plan_.data()) != NEOMPC_OK)
+      throw nav2_core::ControllerException(std::string("neompc_local_plan failed: ") + neompc_last_error(mpc_));
+  }
+
   geometry_msgs::msg::TwistStamped cmd_vel_final;
   cmd_vel_final.header.frame_id = costmap_ros_->getBaseFrameID();
   cmd_vel_final.twist.linear.x = last_response_.vx;

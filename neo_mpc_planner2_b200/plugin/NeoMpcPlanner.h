@@ -45,6 +45,7 @@ public:
   // diagnostics of the last solve (what the reference published as local_plan, srv.py:365)
   const std::vector<float> & lastPlan() const { return last_plan_; }
   const neompc_response & lastResponse() const { return last_response_; }
+  const std::vector<neompc_plan_pose> & lastLocalPlan() const { return last_local_plan_; }   // poses of /mpc_local_plan
 
 private:
   geometry_msgs::msg::PoseStamped pickCarrot(const geometry_msgs::msg::PoseStamped & robot, double lookahead);
@@ -65,6 +66,7 @@ private:
   neompc_handle * mpc_ = nullptr;        // replaces rclcpp::Client<neo_srvs2::srv::Optimizer> (reference h:150)
   neompc_params params_{};
   std::vector<float> last_plan_;
+  std::vector<neompc_plan_pose> last_local_plan_;
   neompc_response last_response_{};
   std::mutex mutex_;
 };
