@@ -293,6 +293,26 @@ def run_ours(args):
     e2e_value = world * n * e2e_steps / float(t.item())
     clocks = sampler.stop()
 
+    # ---- latency of ONE request through the message-level entry (what the controller plugin calls every tick,
+    # replacing the ROS service hop + scipy solve): neompc_solve_msgs, stateful instance 0, host buffers
+    lat = None
+    if rank == 0:
+        from neo_mpc_planner2_b200.server import requests_to_msgs
+        solver.reserve_instances(1)
+        msg = requests_to_msgs(wl.requests[:1])
+        msg["instance_id"] = 0
+        msg["delta_t"] = 1.0 / 30.0
+        for _ in range(20):
+            solver.solve_msgs(msg)
+        ts = []
+        for _ in range(200):
+            solver.reset_state()                                  # cold start every time, like the batch numbers
+            t1 = time.perf_counter()
+            solver.solve_msgs(msg)
+            ts.append(time.perf_counter() - t1)
+        lat = {"n": 1, "api": "neompc_solve_msgs (pack + solve + D2H, cold start)", "median_us": 1e6 * float(np.median(ts)),
+               "p99_us": 1e6 * float(np.percentile(ts, 99))}
+
     resp = np.frombuffer(resp_host.numpy().tobytes(), dtype=RESPONSE_DTYPE)
     iters_med = float(np.median(resp["iters"]))
     evals_mean = float(resp["evals"].mean())
@@ -337,6 +357,7 @@ def run_ours(args):
                     "api": "neompc_solve_batch (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "single_request_latency": lat,
         }
         if world == 1 and not args.no_cpu_baseline and not args.footprint_mode:
             # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)

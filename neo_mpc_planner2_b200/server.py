@@ -147,7 +147,7 @@ class MpcOptimizationServer:
     def cb_params(self, **changes):
         """Dynamic parameter update (srv.py:405-439)."""
         self.params.update(changes)
-        self._solver.set_params(self.params)
+        self._solver.set_params(**changes)
 
     # -- the service handler
     def optimizer(self, request, response=None):

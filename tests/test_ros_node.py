@@ -1,0 +1,121 @@
+"""The ROS 2 node shim for un-modified clients, exercised under the stand-in ROS modules of
+tests/golden/ros_stubs.py (this image has no rclpy): same node name, service, topics and parameter names as the
+reference; answers equal the library's direct answers; the published Path equals the oracle's publishLocalPlan."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+import oracle
+from neo_mpc_planner2_b200 import workloads
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture()
+def ros(monkeypatch):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import ros_stubs
+    saved = {k: v for k, v in sys.modules.items()}
+    ros_stubs.install()
+    sys.modules.pop("neo_mpc_planner2_b200.ros_node", None)
+    yield ros_stubs
+    for k in list(sys.modules):
+        if k not in saved:
+            del sys.modules[k]
+    sys.path.remove(os.path.join(HERE, "golden"))
+
+
+class Recorder:
+    def __init__(self):
+        self.msgs = []
+
+    def publish(self, m):
+        self.msgs.append(m)
+
+
+def make_request(S, r):
+    rq = S.OptimizerRequest()
+    rq.current_vel.linear.x, rq.current_vel.linear.y, rq.current_vel.angular.z = (float(r["vel_x"]), float(r["vel_y"]),
+                                                                                   float(r["vel_theta"]))
+    for pose, px, py, yaw in ((rq.carrot_pose.pose, "carrot_x", "carrot_y", "carrot_yaw"),
+                              (rq.goal_pose, "goal_x", "goal_y", "goal_yaw"),
+                              (rq.current_pose.pose, "pose_x", "pose_y", "pose_yaw")):
+        pose.position.x, pose.position.y = float(r[px]), float(r[py])
+        q = oracle.quat_from_yaw(float(r[yaw]))
+        pose.orientation.x, pose.orientation.y, pose.orientation.z, pose.orientation.w = q
+    rq.control_interval = float(r["control_interval"])
+    return rq
+
+
+def test_node_module_mirrors_reference_interface(ros):
+    """Importable under the ROS stand-ins; parameter names and defaults are the reference's (srv.py:49-75)."""
+    from neo_mpc_planner2_b200 import ros_node
+    assert ros_node.REFERENCE_PARAMETERS == oracle.MpcParams().as_dict()
+    assert set(ros_node.EFFECTIVE_IN_REFERENCE) <= set(ros_node.DYNAMIC_NAMES) <= set(ros_node.REFERENCE_PARAMETERS)
+    assert issubclass(ros_node.MpcOptimizationServer, ros.Node)
+
+
+@pytest.mark.gpu
+def test_node_answers_like_the_library(ros):
+    from neo_mpc_planner2_b200 import ros_node
+    from neo_mpc_planner2_b200.solver import BatchSolver
+    from oracle.mpc_oracle import footprint_world
+    wl = workloads.config("c2", batch=64)
+    created = {}
+    orig_service = ros.Node.create_service
+    ros.Node.create_service = lambda self, typ, name, cb: created.setdefault("service", (typ, name, cb))
+    subs = {}
+    ros.Node.create_subscription = lambda self, typ, topic, cb, depth: subs.setdefault(topic, cb)
+    try:
+        ros.PARAM_OVERRIDES.update(wl.params)
+        node = ros_node.MpcOptimizationServer()
+        ros.PARAM_OVERRIDES.clear()
+    finally:
+        ros.Node.create_service = orig_service
+    assert created["service"][0] is ros.Optimizer and created["service"][1] == "optimizer"
+    assert set(subs) == {"/local_costmap/published_footprint", "/local_costmap/costmap"}
+    node.PubRaysPath = Recorder()
+    # costmap and footprint arrive on their topics
+    grid = types.SimpleNamespace(
+        info=types.SimpleNamespace(width=wl.cells.shape[1], height=wl.cells.shape[0], resolution=wl.resolution,
+                                   origin=types.SimpleNamespace(position=types.SimpleNamespace(x=wl.origin_x, y=wl.origin_y))),
+        data=wl.cells.astype(np.int8).ravel().tolist())
+    subs["/local_costmap/costmap"](grid)
+    p = oracle.MpcParams(**wl.params)
+    with BatchSolver(wl.params) as direct:
+        direct.load_workload(wl)
+        direct.reserve_instances(1)
+        for k in (0, 5, 9):
+            r = wl.requests[k]
+            fpw = footprint_world(wl.footprint, float(r["pose_x"]), float(r["pose_y"]), float(r["pose_yaw"]))
+            subs["/local_costmap/published_footprint"](
+                ros.PolygonStamped(polygon=ros.Polygon(points=[ros.Point32(x, y, 0.0) for x, y in fpw])))
+            resp = created["service"][2](make_request(ros, r), ros.OptimizerResponse())
+            one = wl.requests[k:k + 1].copy()
+            one["instance_id"] = 0
+            one["delta_t"] = 1e9                      # first call / new goal each time
+            direct.reset_state()
+            want, plan = direct.solve(one, want_plan=True)
+            got = (resp.output_vel.twist.linear.x, resp.output_vel.twist.linear.y, resp.output_vel.twist.angular.z)
+            assert np.abs(np.array(got) - np.array([want["vx"][0], want["vy"][0], want["omega"][0]])).max() <= 2e-4
+            path = node.PubRaysPath.msgs[-1]
+            assert path.header.frame_id == "map" and len(path.poses) == p.control_steps + 1
+            mine = oracle.local_plan(p, float(r["pose_x"]), float(r["pose_y"]),
+                                     oracle.euler_yaw(*oracle.quat_from_yaw(float(r["pose_yaw"]))), node.solution.astype(np.float64))
+            got_path = np.array([[ps.pose.position.x, ps.pose.position.y, ps.pose.orientation.z, ps.pose.orientation.w]
+                                 for ps in path.poses])
+            assert np.abs(got_path - mine).max() <= 1e-5
+    # dynamic parameters: the reference's callback semantics (srv.py:405-439)
+    P = ros.Parameter
+    mk = lambda n, v, t=P.Type.DOUBLE: types.SimpleNamespace(name=n, value=v, type_=t)
+    res = node.cb_params([mk("w_trans", 1.5), mk("max_vel_x", 0.2), mk("w_costmap", 9.0), mk("w_orient", 0.9, 2)])
+    assert res.successful
+    assert node.params["w_trans"] == 1.5
+    assert node.params["max_vel_x"] == wl.params["max_vel_x"]      # bounds are built once in the reference (srv.py:125-133)
+    assert node.params["w_costmap"] == wl.params["w_costmap"]      # copied to w_costmap_scale at start-up (srv.py:96)
+    assert node.params["w_orient"] == wl.params["w_orient"]        # not a DOUBLE: ignored (srv.py:407)
+    assert float(node._solver.params["w_trans"]) == 1.5
+    node.destroy_node()
