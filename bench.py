@@ -330,10 +330,18 @@ def run_ours(args):
         achieved = bytes_per_solve * n / (k_ms * 1e-3) / 1e9
         wl_name, _ = _workload_name(args.config)
         traffic = None            # dram bytes per launch from the committed ncu capture of the same kernel/config
+        issue = None              # the ceiling that actually binds: warp-instruction issue rate (SURVEY §7 hard part 6)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
-            if tr and tr["kernel"] == f"solve_kernel<{G},{S}>" and tr["batch"] == n:
+            if tr and tr["kernel"] == f"solve_kernel<{G},{S}>" and tr["batch"] == n and not args.footprint_mode:
                 traffic = tr["dram_bytes_per_launch"]
+                sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+                peak_issue = sm_count * 4 * mhz * 1e6            # 4 schedulers per SM, one warp instruction per clock each
+                ach_issue = tr["inst_executed"] / (k_ms * 1e-3)  # instruction count of the committed capture / live time
+                issue = {"achieved_gwarp_inst_per_s": ach_issue / 1e9, "peak_gwarp_inst_per_s": peak_issue / 1e9,
+                         "frac": ach_issue / peak_issue, "warp_inst_per_launch": tr["inst_executed"],
+                         "source": "inst_executed from profiles/solve_kernel_r1_summary.md (ncu), time measured live"}
         except Exception:
             pass
         line = {
@@ -351,6 +359,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
                          "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
+                         "issue_slots": issue,
                          "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * REQUEST_DTYPE.itemsize),
                     "d2h_bytes_per_step": int(n * RESPONSE_DTYPE.itemsize), "ms_per_step": 1e3 * e2e_s / e2e_steps,
