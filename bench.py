@@ -162,7 +162,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def stop(self):
         self._halt.set()
