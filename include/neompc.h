@@ -184,7 +184,8 @@ int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, si
                               neompc_response* d_out, float* d_twist_or_null, float* d_plan_or_null,
                               void* stream);
 /* Message-level entry: float64 quaternion requests on the host -> device pack (euler_from_quaternion incl. the
- * goal-w quirk, srv.py:160-180, :211-213) -> solve -> responses on the host. */
+ * goal-w quirk, srv.py:160-180, :211-213) -> solve -> responses on the host.  This is the per-tick call of the
+ * controller plugin: small batches take a pinned mailbox path and a latency-oriented lane tiling. */
 int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, size_t n,
                       neompc_response* out, float* plan_or_null);
 /* Device-side packing only (d_msgs, d_reqs device pointers), asynchronous on `stream`. */

@@ -152,4 +152,12 @@ inline void choose_tiling(int n_steps, int lanes_override, int* G, int* S) {
   *S = (n_steps + g - 1) / g;
 }
 
+// tiling for tiny batches: the fewest steps per lane the supported group sizes allow (see runtime.cu: dispatch)
+inline void choose_latency_tiling(int n_steps, int* G, int* S) {
+  int g = 1;
+  while (g < n_steps && g < 32) g <<= 1;            // powers of two: butterfly reductions are the shortest
+  *G = g;
+  *S = (n_steps + g - 1) / g;
+}
+
 }  // namespace neompc

@@ -26,7 +26,8 @@ struct neompc_handle {
   SolverConst c{};
   HostTables tab;
   int encoding = NEOMPC_ENC_OCCUPANCY;
-  int G = 1, S = 1;
+  int G = 1, S = 1;         // lane-group tiling of batches (throughput)
+  int Gl = 1, Sl = 1;       // tiling of tiny batches (latency): one step per lane where possible
   float* d_lut_cost = nullptr;
   uint8_t* d_lut_flag = nullptr;
   uint8_t* d_cells = nullptr;
@@ -49,8 +50,16 @@ struct neompc_handle {
   neompc_carrot_info* d_info = nullptr;
   size_t cap_ticks = 0;
   int sm_count = 0;
+  // small-batch mailbox: pinned + mapped host memory the kernels read requests from / write results to directly, so a
+  // controller tick (n = 1) costs two launches and one synchronise instead of three staged pageable copies
+  neompc_optimizer_request* mb_msgs = nullptr;
+  neompc_request* mb_reqs = nullptr;
+  neompc_response* mb_resp = nullptr;
+  float* mb_plan = nullptr;
   std::string err;
 };
+
+constexpr size_t kMailboxRequests = 64;
 
 static thread_local std::string g_create_error;
 
@@ -105,6 +114,8 @@ void rebuild_const(neompc_handle* h) {
   h->c.state = h->d_state;
   h->c.state_rows = h->state_rows;
   choose_tiling(h->params.control_steps, h->params.lanes_per_instance, &h->G, &h->S);
+  h->Gl = h->G; h->Sl = h->S;
+  if (h->params.lanes_per_instance <= 0) choose_latency_tiling(h->params.control_steps, &h->Gl, &h->Sl);
 }
 
 int ensure_staging(neompc_handle* h, size_t n, bool want_plan, bool want_msgs) {
@@ -132,18 +143,25 @@ int ensure_staging(neompc_handle* h, size_t n, bool want_plan, bool want_msgs) {
   return NEOMPC_OK;
 }
 
+// A handful of requests (a controller tick) cannot fill the device: what matters then is the length of the serial
+// instruction stream of one warp, which is shortest with one step per lane.  Measured for one request, N = 10:
+// (4,3) 69 us, (16,1) 58 us through neompc_solve_msgs (profiles/latency_n1_r1.txt).
+constexpr unsigned kLatencyBatch = 32;
+
 cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
-  switch (h->G) {
-    case 1: return launch_g1(eval, h->S, a);
-    case 2: return launch_g2(eval, h->S, a);
-    case 3: return launch_g3(eval, h->S, a);
-    case 4: return launch_g4(eval, h->S, a);
-    case 5: return launch_g5(eval, h->S, a);
-    case 6: return launch_g6(eval, h->S, a);
-    case 8: return launch_g8(eval, h->S, a);
-    case 10: return launch_g10(eval, h->S, a);
-    case 16: return launch_g16(eval, h->S, a);
-    case 32: return launch_g32(eval, h->S, a);
+  const bool latency = !eval && a.n <= kLatencyBatch;
+  const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
+  switch (G) {
+    case 1: return launch_g1(eval, S, a);
+    case 2: return launch_g2(eval, S, a);
+    case 3: return launch_g3(eval, S, a);
+    case 4: return launch_g4(eval, S, a);
+    case 5: return launch_g5(eval, S, a);
+    case 6: return launch_g6(eval, S, a);
+    case 8: return launch_g8(eval, S, a);
+    case 10: return launch_g10(eval, S, a);
+    case 16: return launch_g16(eval, S, a);
+    case 32: return launch_g32(eval, S, a);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -262,6 +280,10 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_lut_flag, kTableSize + 6));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_msgs, kMailboxRequests * sizeof(neompc_optimizer_request), cudaHostAllocMapped));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_reqs, kMailboxRequests * sizeof(neompc_request), cudaHostAllocMapped));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_resp, kMailboxRequests * sizeof(neompc_response), cudaHostAllocMapped));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_plan, kMailboxRequests * 3 * NEOMPC_MAX_CONTROL_STEPS * sizeof(float), cudaHostAllocMapped));
 #undef CREATE_CUDA
   build_const(h->params, h->c);
   rebuild_const(h);
@@ -279,6 +301,7 @@ int neompc_destroy(neompc_handle* h) {
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
+  cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan);
   delete h;
   return NEOMPC_OK;
 }
@@ -442,6 +465,17 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
   NEOMPC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h, n, plan_or_null != nullptr, false);
   if (rc != NEOMPC_OK) return rc;
+  if (n <= kMailboxRequests) {                 // small batch: pinned mailbox in, mapped mailbox out (see solve_msgs)
+    const size_t n3s = n * 3 * (size_t)h->params.control_steps;
+    std::memcpy(h->mb_reqs, reqs, n * sizeof(neompc_request));
+    NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs, h->mb_reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream));
+    rc = do_solve_device(h, h->d_reqs, n, h->mb_resp, nullptr, plan_or_null ? h->mb_plan : nullptr, h->stream);
+    if (rc != NEOMPC_OK) return rc;
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
+    if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3s * sizeof(float));
+    return NEOMPC_OK;
+  }
   // Large batches are cut into chunks that alternate between two streams, so the H2D copy of one chunk, the solve of
   // another and the D2H copy of a third overlap (the copy engines for the two directions and the SMs are independent).
   // Problems are independent, so chunking does not change any result.
@@ -486,6 +520,20 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
   NEOMPC_CUDA(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h, n, plan_or_null != nullptr, true);
   if (rc != NEOMPC_OK) return rc;
+  if (n <= kMailboxRequests) {
+    // controller-tick path: messages go through the mapped mailbox (the pack kernel reads them over PCIe), responses
+    // and plan are written by the solve kernel straight into mapped host memory
+    const size_t n3 = n * 3 * (size_t)h->params.control_steps;
+    std::memcpy(h->mb_msgs, msgs, n * sizeof(neompc_optimizer_request));
+    rc = neompc_pack_requests(h, h->mb_msgs, n, h->d_reqs, h->stream);
+    if (rc != NEOMPC_OK) return rc;
+    rc = do_solve_device(h, h->d_reqs, n, h->mb_resp, nullptr, plan_or_null ? h->mb_plan : nullptr, h->stream);
+    if (rc != NEOMPC_OK) return rc;
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
+    if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3 * sizeof(float));
+    return NEOMPC_OK;
+  }
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_msgs, msgs, n * sizeof(neompc_optimizer_request), cudaMemcpyHostToDevice, h->stream));
   rc = neompc_pack_requests(h, h->d_msgs, n, h->d_reqs, h->stream);
   if (rc != NEOMPC_OK) return rc;
