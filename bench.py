@@ -198,7 +198,8 @@ def run_ours(args):
     wl = workloads.config(args.config, batch=per_gpu, seed=None if rank == 0 else 1000 + rank)
     n = wl.batch
     n_steps = wl.control_steps
-    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode)
+    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode,
+                         costmap_mode=args.costmap_mode)
     solver.load_workload(wl)
     G, S = solver.tiling
 
@@ -333,7 +334,7 @@ def run_ours(args):
         issue = None              # the ceiling that actually binds: warp-instruction issue rate (SURVEY §7 hard part 6)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
-            if tr and tr["kernel"] == f"solve_kernel<{G},{S}>" and tr["batch"] == n and not args.footprint_mode:
+            if tr and tr["kernel"] == f"solve_kernel<{G},{S}>" and tr["batch"] == n and not args.footprint_mode and not args.costmap_mode:
                 traffic = tr["dram_bytes_per_launch"]
                 sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
                 mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
@@ -355,6 +356,7 @@ def run_ours(args):
                                       "overlapped with the next step's solve on a second stream"
                        if world > 1 else "single GPU", "cold_start": True,
                        "footprint_mode": "moving (opt-in, not the reference's objective)" if args.footprint_mode else "static (reference)",
+                       "costmap_mode": "bilinear (opt-in, not the reference's objective)" if args.costmap_mode else "nearest cell (reference)",
                        "iters_median": iters_med, "evals_mean": evals_mean},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
@@ -368,7 +370,7 @@ def run_ours(args):
             "clocks": clocks,
             "single_request_latency": lat,
         }
-        if world == 1 and not args.no_cpu_baseline and not args.footprint_mode:
+        if world == 1 and not args.no_cpu_baseline and not args.footprint_mode and not args.costmap_mode:
             # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)
             import subprocess
             sample = args.cpu_sample or {"c2": 2048, "c3": 256, "c4": 64, "c5": 256}[args.config]   # ~15 core-seconds
@@ -427,6 +429,9 @@ def main():
     ap.add_argument("--footprint-mode", type=int, default=0, choices=[0, 1],
                     help="0 = the reference's static footprint term (default, parity mode); 1 = opt-in moving footprint "
                          "(SURVEY 8f row N1; no CPU baseline / cost residual for it)")
+    ap.add_argument("--costmap-mode", type=int, default=0, choices=[0, 1],
+                    help="0 = the reference's nearest-cell costmap term (default, parity mode); 1 = opt-in bilinear term "
+                         "with gradient (SURVEY 8f row N4; no CPU baseline / cost residual for it)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ref", default="", help="reference arm: save per-problem J and x of the last pass (npz)")

@@ -39,6 +39,18 @@ enum {
   NEOMPC_FOOTPRINT_MOVING = 1
 };
 
+/* neompc_params.costmap_mode: how the costmap term of the objective (srv.py:246-247, 257-260) samples the grid.
+ * NEAREST reproduces the reference: the cost of the cell containing the predicted position; the term is piecewise
+ * constant, so neither scipy's finite differences nor the analytic gradient here see the obstacles.
+ * BILINEAR (changes results, hence opt-in) interpolates between the four nearest cell
+ * centres: c = bilerp(cell cost), l = bilerp(cell cost == 1.0), term = (w_costmap c^2 + (1000 - w_costmap) l^2) / N.
+ * At a cell centre this equals the reference's term; in between it is smooth and its gradient enters the solver, so
+ * plans bend away from inflated obstacles.  collision_check (srv.py:312-347) stays on the nearest cell in both modes. */
+enum {
+  NEOMPC_COSTMAP_NEAREST = 0,
+  NEOMPC_COSTMAP_BILINEAR = 1
+};
+
 /* error codes */
 enum {
   NEOMPC_OK = 0,
@@ -76,7 +88,8 @@ typedef struct neompc_params {
   float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254); default 1e-2 */
   int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
   int32_t footprint_mode;      /* NEOMPC_FOOTPRINT_* ; 0 = the reference's behaviour */
-  int32_t reserved[5];
+  int32_t costmap_mode;        /* NEOMPC_COSTMAP_* ; 0 = the reference's behaviour */
+  int32_t reserved[4];
 } neompc_params;
 
 /*

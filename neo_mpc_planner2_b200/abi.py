@@ -79,6 +79,10 @@ ENC_NAV2_RAW = 1
 FOOTPRINT_STATIC = 0          # the reference: the polygon never moves (aliasing at srv.py:227,241-244)
 FOOTPRINT_MOVING = 1          # opt-in: polygon placed at every predicted pose
 
+# neompc_params.costmap_mode
+COSTMAP_NEAREST = 0           # the reference: cost of the cell under the predicted position
+COSTMAP_BILINEAR = 1          # opt-in: bilinear interpolation between cell centres, gradient enters the solver (row N4)
+
 # neompc_params — the reference's 22 server parameters (srv.py:49-75) + solver knobs
 PARAMS_FIELDS = [
     ("acc_x_limit", "<f4"), ("acc_y_limit", "<f4"), ("acc_theta_limit", "<f4"),
@@ -95,7 +99,8 @@ PARAMS_FIELDS = [
     ("control_smoothing", "<f4"),
     ("lanes_per_instance", "<i4"),
     ("footprint_mode", "<i4"),
-    ("reserved", "<i4", (5,)),
+    ("costmap_mode", "<i4"),
+    ("reserved", "<i4", (4,)),
 ]
 PARAMS_DTYPE = np.dtype(PARAMS_FIELDS, align=False)
 assert PARAMS_DTYPE.itemsize == 128

@@ -1,6 +1,6 @@
 // kernels.cuh — __global__ wrappers around the lane-group solver core (mpc_core.cuh) and their launchers.
 // One translation unit per lanes-per-instance value G (solve_g1.cu ... solve_g32.cu; G = 1,2,3,4,5,6,8,10,16,32)
-// instantiates S = 1..6.
+// instantiates S = 1..4, each with and without the opt-in objective extensions.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -13,7 +13,7 @@ namespace neompc {
 #define NEOMPC_BLOCK_THREADS 64
 #endif
 constexpr int kBlockThreads = NEOMPC_BLOCK_THREADS;      // kBlockThreads/G instances per block
-constexpr int kMaxStepsPerLane = 6;
+constexpr int kMaxStepsPerLane = 4;
 
 struct LaunchArgs {
   SolverConst P;
@@ -84,7 +84,7 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 #endif
 // resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
 constexpr int min_blocks_for(int S) {
-  return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : S == 4 ? 3 : 2) * (128 / kBlockThreads);
+  return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : 3) * (128 / kBlockThreads);
 }
 
 // ---- TMA (bulk async copy) staging of the block's request tile ------------------------------------------------
@@ -119,7 +119,7 @@ __device__ __forceinline__ void tma_stage_requests(neompc_request* s_req, unsign
   }
 }
 
-template <int G, int S>
+template <int G, int S, bool X>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
 solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
              const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
@@ -148,13 +148,13 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   const unsigned inst = first + gm.slot;
   const bool valid = gm.lane_ok && inst < n;
   const neompc_request& rq = s_req[gm.slot];
-  solve_instance<G, S>(P, T, rq, valid, gm.lg, hist_smem + threadIdx.x, kBlockThreads,
+  solve_instance<G, S, X>(P, T, rq, valid, gm.lg, hist_smem + threadIdx.x, kBlockThreads,
                        valid ? out + inst : nullptr,
                        (valid && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,
                        (valid && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
 }
 
-template <int G, int S>
+template <int G, int S, bool X>
 __global__ void __launch_bounds__(kBlockThreads)
 eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
             const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
@@ -168,54 +168,58 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
   const int lg = gm.lg;
   const bool valid = gm.lane_ok && inst < n;
   const neompc_request rq = load_request(reqs, inst, valid);
-  eval_instance<G, S>(P, T, rq, valid, lg, valid ? u + (size_t)inst * 3 * P.N : nullptr,
+  eval_instance<G, S, X>(P, T, rq, valid, lg, valid ? u + (size_t)inst * 3 * P.N : nullptr,
                       valid ? J + inst : nullptr,
                       (valid && grad != nullptr) ? grad + (size_t)inst * 3 * P.N : nullptr);
 }
 
-template <int G, int S>
+template <int G, int S, bool X>
 cudaError_t launch_solve_gs(const LaunchArgs& a) {
   const size_t smem = (size_t)kBlockThreads * hist_floats_per_lane<S>(a.P.m) * sizeof(float);
   constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const unsigned blocks_needed = (a.n + kInstPerBlock - 1) / kInstPerBlock;
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  solve_kernel<G, S><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
+  solve_kernel<G, S, X><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
                                                                        a.twist, a.plan);
   return cudaGetLastError();
 }
 
-template <int G, int S>
+template <int G, int S, bool X>
 cudaError_t launch_eval_gs(const LaunchArgs& a) {
   constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const unsigned grid = (a.n + kInstPerBlock - 1) / kInstPerBlock;
-  eval_kernel<G, S><<<grid, kBlockThreads, 0, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.u, a.J, a.grad);
+  eval_kernel<G, S, X><<<grid, kBlockThreads, 0, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.u, a.J, a.grad);
   return cudaGetLastError();
 }
 
-template <int G>
-cudaError_t launch_for_g(bool eval, int S, const LaunchArgs& a) {
+// ext: the handle's parameters select an opt-in objective extension (moving footprint / bilinear costmap)
+template <int G, bool X>
+cudaError_t launch_for_gx(bool eval, int S, const LaunchArgs& a) {
   switch (S) {
-    case 1: return eval ? launch_eval_gs<G, 1>(a) : launch_solve_gs<G, 1>(a);
-    case 2: return eval ? launch_eval_gs<G, 2>(a) : launch_solve_gs<G, 2>(a);
-    case 3: return eval ? launch_eval_gs<G, 3>(a) : launch_solve_gs<G, 3>(a);
-    case 4: return eval ? launch_eval_gs<G, 4>(a) : launch_solve_gs<G, 4>(a);
-    case 5: return eval ? launch_eval_gs<G, 5>(a) : launch_solve_gs<G, 5>(a);
-    case 6: return eval ? launch_eval_gs<G, 6>(a) : launch_solve_gs<G, 6>(a);
+    case 1: return eval ? launch_eval_gs<G, 1, X>(a) : launch_solve_gs<G, 1, X>(a);
+    case 2: return eval ? launch_eval_gs<G, 2, X>(a) : launch_solve_gs<G, 2, X>(a);
+    case 3: return eval ? launch_eval_gs<G, 3, X>(a) : launch_solve_gs<G, 3, X>(a);
+    case 4: return eval ? launch_eval_gs<G, 4, X>(a) : launch_solve_gs<G, 4, X>(a);
     default: return cudaErrorInvalidValue;
   }
 }
 
+template <int G>
+cudaError_t launch_for_g(bool eval, int S, bool ext, const LaunchArgs& a) {
+  return ext ? launch_for_gx<G, true>(eval, S, a) : launch_for_gx<G, false>(eval, S, a);
+}
+
 // defined in solve_g*.cu
-cudaError_t launch_g1(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g2(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g3(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g4(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g5(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g6(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g8(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g10(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g16(bool eval, int S, const LaunchArgs& a);
-cudaError_t launch_g32(bool eval, int S, const LaunchArgs& a);
+cudaError_t launch_g1(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g2(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g3(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g4(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g5(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g6(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g8(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g10(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g16(bool eval, int S, bool ext, const LaunchArgs& a);
+cudaError_t launch_g32(bool eval, int S, bool ext, const LaunchArgs& a);
 
 }  // namespace neompc

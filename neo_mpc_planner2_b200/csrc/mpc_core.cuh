@@ -65,6 +65,10 @@ struct SolverConst {
   float w_fp;          // w_footprint: N * (1.0^2 * w_footprint / N)  (srv.py:263); 0 in the moving-footprint mode
   float w_fp_step;     // moving-footprint mode (NEOMPC_FOOTPRINT_MOVING): w_footprint / N per lethal step, else 0
   int fp_mode;         // neompc_params.footprint_mode
+  int cm_mode;         // neompc_params.costmap_mode
+  float cm_scale;      // 1 / lethal_byte: cell byte -> normalised cost (bilinear mode)
+  float cm_w;          // w_costmap / N                               (bilinear mode)
+  float cm_wl;         // (1000 - w_costmap) / N                      (bilinear mode)
   int lethal_byte;     // the cell byte whose cost is 1.0 in the current encoding (100 or 254)
   float eps2;          // control_smoothing^2
   float lo[3], hi[3];  // box (srv.py:127-129)
@@ -350,7 +354,9 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
   return c;
 }
 
-template <int G, int S>
+// X = true compiles the opt-in objective extensions (moving footprint, bilinear costmap) in; the reference-mode
+// kernels are instantiated with X = false so that their hot loop carries none of that code (it cost 7-20 % there).
+template <int G, int S, bool X>
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
 
@@ -376,6 +382,42 @@ struct Forward {
     const int cell = (int)P.cells[idx];
 #endif
     return inb ? cell : kCellOob;
+  }
+
+  // Bilinear costmap mode (NEOMPC_COSTMAP_BILINEAR).  Normalised cost c and lethal indicator l are
+  // interpolated between the four cell centres around the predicted position; term = cm_w c^2 + cm_wl l^2.
+  // Returns the term; (dx, dy) receive its derivative w.r.t. the BASE-frame rollout offset (x, y) in metres
+  // (chain rule through the rotation by the start yaw; I.cq / I.sq carry the factor 1/resolution).
+  static NEOMPC_HD float bilinear_term(const SolverConst& P, const Instance& I, float x, float y, float* dx, float* dy) {
+    const float gx = I.fx + (I.cq * x - I.sq * y) - 0.5f;          // cell-centre coordinates relative to the base cell
+    const float gy = I.fy + (I.sq * x + I.cq * y) - 0.5f;
+    const float fx0 = floorf(gx), fy0 = floorf(gy);
+    const float tx = gx - fx0, ty = gy - fy0;
+    const int mx = I.bx + (int)fx0, my = I.by + (int)fy0;
+    float c[4], l[4];
+    NEOMPC_UNROLL
+    for (int q = 0; q < 4; ++q) {
+      const int cx = mx + (q & 1), cy = my + (q >> 1);
+      const bool inb = (unsigned)cx < (unsigned)P.W && (unsigned)cy < (unsigned)P.H;
+      const unsigned idx = inb ? (unsigned)cy * (unsigned)P.W + (unsigned)cx : 0u;
+#if defined(__CUDA_ARCH__)
+      const int b = (int)__ldg(P.cells + idx);
+#else
+      const int b = (int)P.cells[idx];
+#endif
+      c[q] = !inb ? 1.0f : (b <= P.lethal_byte ? (float)b * P.cm_scale : 0.0f);    // outside the map: lethal
+      l[q] = (!inb || b == P.lethal_byte) ? 1.0f : 0.0f;
+    }
+    const float c0 = c[0] + tx * (c[1] - c[0]), c1 = c[2] + tx * (c[3] - c[2]);
+    const float l0 = l[0] + tx * (l[1] - l[0]), l1 = l[2] + tx * (l[3] - l[2]);
+    const float cv = c0 + ty * (c1 - c0), lv = l0 + ty * (l1 - l0);
+    const float dcx = (c[1] - c[0]) + ty * ((c[3] - c[2]) - (c[1] - c[0])), dcy = c1 - c0;   // per cell
+    const float dlx = (l[1] - l[0]) + ty * ((l[3] - l[2]) - (l[1] - l[0])), dly = l1 - l0;
+    const float ggx = 2.0f * (P.cm_w * cv * dcx + P.cm_wl * lv * dlx);                       // d term / d gx
+    const float ggy = 2.0f * (P.cm_w * cv * dcy + P.cm_wl * lv * dly);
+    *dx = ggx * I.cq + ggy * I.sq;                                                           // gx = .. + cq x - sq y
+    *dy = -ggx * I.sq + ggy * I.cq;                                                          // gy = .. + sq x + cq y
+    return P.cm_w * cv * cv + P.cm_wl * lv * lv;
   }
 
   // Moving-footprint mode (NEOMPC_FOOTPRINT_MOVING): is the robot-frame polygon, placed at the
@@ -468,12 +510,20 @@ struct Forward {
   // This lane's share of J (srv.py:246-268) for the rollout held in the struct.  The control term uses
   // sqrt(r^2 + eps^2); its reciprocal is kept for backward().
   NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg) {
+    const bool bilinear = X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr;   // uniform
     int cell[S];
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j)                                                     // srv.py:246-247 via :234-236
-      cell[j] = cell_of(P, I, I.cq, I.sq, x[j], y[j]);                              // (loads issued together)
+      cell[j] = bilinear ? kCellFree : cell_of(P, I, I.cq, I.sq, x[j], y[j]);       // (loads issued together)
     float J = 0.0f;
-    if (P.fp_mode == NEOMPC_FOOTPRINT_MOVING && P.cells != nullptr && P.fp_n > 0) {      // uniform branch
+    if (bilinear) {
+      for (int j = 0; j < S; ++j) {
+        float ddx, ddy;
+        const float t = bilinear_term(P, I, x[j], y[j], &ddx, &ddy);
+        J += (lg * S + j < P.N) ? t : 0.0f;
+      }
+    }
+    if (X && P.fp_mode == NEOMPC_FOOTPRINT_MOVING && P.cells != nullptr && P.fp_n > 0) {      // uniform branch
       for (int j = 0; j < S; ++j) {
         const bool hit = footprint_lethal_at(P, I, x[j], y[j], c[j], s[j]);
         J += (hit && lg * S + j < P.N) ? P.w_fp_step : 0.0f;                        // srv.py:262-263 per step
@@ -514,6 +564,12 @@ struct Forward {
       const bool on = i < P.N;
       gx[j] = on ? -2.0f * P.a_trans * (I.cx - x[j]) : 0.0f;
       gy[j] = on ? -2.0f * P.a_trans * (I.cy - y[j]) : 0.0f;
+      if (X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr) {       // uniform; re-gathers 4 cells (L1 hits)
+        float ddx, ddy;
+        bilinear_term(P, I, x[j], y[j], &ddx, &ddy);
+        gx[j] += on ? ddx : 0.0f;
+        gy[j] += on ? ddy : 0.0f;
+      }
       gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
       gz[j] += (i == P.N - 1) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
       sx += gx[j]; gx[j] = sx;                  // local inclusive suffix sums
@@ -645,7 +701,7 @@ NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], co
 // Every collective (shuffle / vote) in here is executed by all 32 lanes of the warp; per-group decisions are
 // predicates, never branches around a collective.
 // ---------------------------------------------------------------------------------------------------------
-template <int G, int S>
+template <int G, int S, bool X>
 struct Solver {
   static constexpr int PAIR = 6 * S + 2;
   // per-instance constants
@@ -751,7 +807,7 @@ struct Solver {
   // one iteration for every group of the warp (inactive groups compute and discard)
   NEOMPC_HD void pass(const SolverConst& P, const CostTables& T, float* hist, int stride, int lg) {
     const int m = P.m;
-    Forward<G, S> fw;
+    Forward<G, S, X> fw;
     float d[S][3], xt[S][3], r[S][3];
 
     // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
@@ -975,12 +1031,12 @@ struct Solver {
       for (int q = 0; q < 3; ++q) ue[0][q] = ue[0][q] * P.lp_gain + last[q] * (1.0f - P.lp_gain);
     }
     // ---- collision_check: re-roll with the TRUE yaw (srv.py:312-347)
-    Forward<G, S> fw;
+    Forward<G, S, X> fw;
     fw.rollout(P, ue, lg);
     int hit = 0;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      const int cell = Forward<G, S>::cell_of(P, I, ct, st, fw.x[j], fw.y[j]);
+      const int cell = Forward<G, S, X>::cell_of(P, I, ct, st, fw.x[j], fw.y[j]);
       hit |= (lg * S + j < P.N) ? (T.flag[cell] >> 1) & 1 : 0;                          // col >= 0.99, srv.py:338
     }
     hit = Grp<G>::imax(hit);
@@ -1042,17 +1098,17 @@ struct Solver {
 };
 
 // One optimizer() call for the instance owned by this lane group (one instance per group per launch).
-template <int G, int S>
+template <int G, int S, bool X>
 NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid,
                               int lg, float* hist, int stride, neompc_response* resp, float* twist, float* plan) {
-  Solver<G, S> sv;
+  Solver<G, S, X> sv;
   sv.prologue(P, T, rq, valid, lg, hist, stride);
   while (Grp<G>::warp_any(sv.active)) sv.pass(P, T, hist, stride, lg);
   sv.epilogue(P, T, rq, true, lg, resp, twist, plan);
 }
 
 // objective value (reference J, unsmoothed) and gradient (smoothed objective) at a given u — test hook
-template <int G, int S>
+template <int G, int S, bool X>
 NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
                              const float* uin, float* Jout, float* gout) {
   Instance I;
@@ -1080,7 +1136,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
     u[j][1] = ld ? uin[3 * i + 1] : 0.0f;
     u[j][2] = ld ? uin[3 * i + 2] : 0.0f;
   }
-  Forward<G, S> fw;
+  Forward<G, S, X> fw;
   const float f = Grp<G>::sum(fw.run(P, T, I, u, lg));
   const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + constant_cost(P, rq, fp_hit);
   fw.backward(P, I, u, lg, g);

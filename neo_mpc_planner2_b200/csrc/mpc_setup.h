@@ -55,6 +55,10 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
   }
   if (p.lbfgs_memory < 0 || p.lbfgs_memory > kMaxMemory) { err = "lbfgs_memory must be 0..8"; return false; }
   if (p.max_iterations < 0) { err = "max_iterations must be >= 0"; return false; }
+  if (p.costmap_mode != NEOMPC_COSTMAP_NEAREST && p.costmap_mode != NEOMPC_COSTMAP_BILINEAR) {
+    err = "costmap_mode must be NEOMPC_COSTMAP_NEAREST or NEOMPC_COSTMAP_BILINEAR";
+    return false;
+  }
   if (p.footprint_mode != NEOMPC_FOOTPRINT_STATIC && p.footprint_mode != NEOMPC_FOOTPRINT_MOVING) {
     err = "footprint_mode must be NEOMPC_FOOTPRINT_STATIC or NEOMPC_FOOTPRINT_MOVING";
     return false;
@@ -92,6 +96,10 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.w_fp = p.footprint_mode == NEOMPC_FOOTPRINT_MOVING ? 0.0f : p.w_footprint;
   c.w_fp_step = p.footprint_mode == NEOMPC_FOOTPRINT_MOVING ? p.w_footprint / (float)N : 0.0f;
   c.lethal_byte = 100;                            // NEOMPC_ENC_OCCUPANCY; set_costmap updates it with the encoding
+  c.cm_mode = p.costmap_mode;
+  c.cm_scale = 1.0f / 100.0f;                     // likewise updated with the encoding
+  c.cm_w = p.w_costmap / (float)N;
+  c.cm_wl = (1000.0f - p.w_costmap) / (float)N;
   const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f) : 1e-2f;
   c.eps2 = eps * eps;
   c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;
@@ -113,17 +121,17 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.state_rows = 0;
 }
 
-// lanes-per-instance G and steps-per-lane S for a horizon of n steps (G*S >= n, S <= 6).
+// lanes-per-instance G and steps-per-lane S for a horizon of n steps (G*S >= n, S <= 4).
 // Auto mode minimises a cost model fitted to sweeps on B200 (profiles/tiling_sweep_r1b.txt, tiling_sweep_r1c.txt):
 //   time per instance  ~  c(S) * shuffles(G) * lockstep(32/G) / (32/G)
-// c(S): warp instructions of one solver pass with S steps per lane (S >= 5 spills registers); shuffles(G): scans and
+// c(S): warp instructions of one solver pass with S steps per lane (kernels exist for S <= 4; more steps per lane spill registers); shuffles(G): scans and
 // reductions take ceil(log2 G) exchange steps, and a group size that is not a power of two pays ~20 % on top (scan +
 // broadcast instead of butterflies, computed source lanes); lockstep: the groups of a warp wait for the slowest one,
 // which costs more the more groups there are.  Measured: N=10 (4,3) 0.458 ms = (5,2) 0.459 ms, (8,2) 0.537;
 // N=20 (8,3) 1.66 ms, (10,2) 1.73, (16,2) 2.04, (5,4) 2.09; N=3 (1,3) 0.168 ms, (2,2) 0.182, (3,1) 0.200.
 constexpr int kGroupSizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 16, 32};
 inline double tiling_cost(int g, int s) {
-  static const double c[7] = {0.0, 0.35, 0.62, 1.0, 1.55, 2.9, 3.8};
+  static const double c[5] = {0.0, 0.35, 0.62, 1.0, 1.55};
   int lg2 = 0;
   while ((1 << lg2) < g) ++lg2;
   const bool pow2 = (g & (g - 1)) == 0;
@@ -139,14 +147,14 @@ inline void choose_tiling(int n_steps, int lanes_override, int* G, int* S) {
     double best = 1e300;
     for (int cand : kGroupSizes) {
       const int s = (n_steps + cand - 1) / cand;
-      if (s > 6) continue;
+      if (s > 4) continue;
       const double t = tiling_cost(cand, s);
       if (t < best) { best = t; g = cand; }
     }
   } else {
-    // a requested group size that would need more than 6 steps per lane: next larger size that fits
+    // a requested group size that would need more than 4 steps per lane: next larger size that fits
     for (int cand : kGroupSizes)
-      if (cand >= g && (n_steps + cand - 1) / cand <= 6) { g = cand; break; }
+      if (cand >= g && (n_steps + cand - 1) / cand <= 4) { g = cand; break; }
   }
   *G = g;
   *S = (n_steps + g - 1) / g;

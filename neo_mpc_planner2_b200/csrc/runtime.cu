@@ -111,6 +111,7 @@ void rebuild_const(neompc_handle* h) {
   std::memcpy(h->c.fp_x, old.fp_x, sizeof(old.fp_x));
   std::memcpy(h->c.fp_y, old.fp_y, sizeof(old.fp_y));
   h->c.lethal_byte = h->encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
+  h->c.cm_scale = 1.0f / (float)h->c.lethal_byte;
   h->c.state = h->d_state;
   h->c.state_rows = h->state_rows;
   choose_tiling(h->params.control_steps, h->params.lanes_per_instance, &h->G, &h->S);
@@ -151,17 +152,18 @@ constexpr unsigned kLatencyBatch = 32;
 cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   const bool latency = !eval && a.n <= kLatencyBatch;
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
+  const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST;
   switch (G) {
-    case 1: return launch_g1(eval, S, a);
-    case 2: return launch_g2(eval, S, a);
-    case 3: return launch_g3(eval, S, a);
-    case 4: return launch_g4(eval, S, a);
-    case 5: return launch_g5(eval, S, a);
-    case 6: return launch_g6(eval, S, a);
-    case 8: return launch_g8(eval, S, a);
-    case 10: return launch_g10(eval, S, a);
-    case 16: return launch_g16(eval, S, a);
-    case 32: return launch_g32(eval, S, a);
+    case 1: return launch_g1(eval, S, ext, a);
+    case 2: return launch_g2(eval, S, ext, a);
+    case 3: return launch_g3(eval, S, ext, a);
+    case 4: return launch_g4(eval, S, ext, a);
+    case 5: return launch_g5(eval, S, ext, a);
+    case 6: return launch_g6(eval, S, ext, a);
+    case 8: return launch_g8(eval, S, ext, a);
+    case 10: return launch_g10(eval, S, ext, a);
+    case 16: return launch_g16(eval, S, ext, a);
+    case 32: return launch_g32(eval, S, ext, a);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -362,6 +364,7 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
   if (encoding != h->encoding) {
     h->encoding = encoding;
     h->c.lethal_byte = encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
+    h->c.cm_scale = 1.0f / (float)h->c.lethal_byte;
     return upload_tables(h);
   }
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -152,6 +152,40 @@ class GridCostmap:
         c = self.lut[self.cells[myc, mxc]]
         return np.where(oob, 1.0, c)
 
+    def bilinear_at_world(self, wx, wy):
+        """OPT-IN bilinear mode (NEOMPC_COSTMAP_BILINEAR; not the reference's behaviour): normalised cost c and
+        lethal indicator l interpolated between the four cell centres around the world points, with their
+        derivatives w.r.t. the world coordinates.  Out-of-map cells count as lethal (cost 1.0), as in getCost.
+        Returns (c, l, dc_dx, dc_dy, dl_dx, dl_dy), numpy float64 arrays shaped like wx."""
+        wx = np.asarray(wx, dtype=np.float64)
+        wy = np.asarray(wy, dtype=np.float64)
+        gx = (wx - self.origin_x) / self.resolution - 0.5
+        gy = (wy - self.origin_y) / self.resolution - 0.5
+        i0 = np.floor(gx).astype(np.int64)
+        j0 = np.floor(gy).astype(np.int64)
+        tx, ty = gx - i0, gy - j0
+        lethal_byte = 100 if self.encoding == ENC_OCCUPANCY else 254
+
+        def corner(di, dj):
+            cx, cy = i0 + di, j0 + dj
+            inb = (cx >= 0) & (cy >= 0) & (cx < self.width) & (cy < self.height)
+            b = self.cells[np.clip(cy, 0, self.height - 1), np.clip(cx, 0, self.width - 1)]
+            c = np.where(inb, self.lut[b], 1.0)
+            l = np.where(inb, (b == lethal_byte).astype(np.float64), 1.0)
+            return c, l
+        (c00, l00), (c10, l10), (c01, l01), (c11, l11) = corner(0, 0), corner(1, 0), corner(0, 1), corner(1, 1)
+
+        def lerp2(v00, v10, v01, v11):
+            v0 = v00 + tx * (v10 - v00)
+            v1 = v01 + tx * (v11 - v01)
+            v = v0 + ty * (v1 - v0)
+            dvx = ((v10 - v00) + ty * ((v11 - v01) - (v10 - v00))) / self.resolution
+            dvy = (v1 - v0) / self.resolution
+            return v, dvx, dvy
+        c, dcx, dcy = lerp2(c00, c10, c01, c11)
+        l, dlx, dly = lerp2(l00, l10, l01, l11)
+        return c, l, dcx, dcy, dlx, dly
+
     def edge_distance_cells(self, wx, wy):
         """Distance (in cells) of world points to the nearest cell edge — used by parity
         tests to exclude samples where fp32 vs fp64 rounding may flip the cell index."""

@@ -144,7 +144,7 @@ def quirk_yaw(pose_quat, goal_quat):
 # --------------------------------------------------------------------------------------
 # objective (srv.py:204-269) and constraint (srv.py:157-158): scalar, bit-exact restatement
 # --------------------------------------------------------------------------------------
-def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel, moving_footprint=None):
+def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel, moving_footprint=None, bilinear=False):
     """J(cmd_vel).  ``footprint_world`` is the polygon the reference holds in
     ``self.footprint`` (world-frame vertices, list of (x, y)); because of the aliasing at
     srv.py:227/241-244 it never moves, so its cost is the same at every step.
@@ -154,7 +154,11 @@ def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel, moving
     ``moving_footprint`` (robot-frame vertices) selects the OPT-IN mode NEOMPC_FOOTPRINT_MOVING
      — NOT the reference's behaviour: the polygon is placed at each predicted
     pose (pos_x, pos_y, odom_yaw) of the costmap rollout (srv.py:234-236), which is what the loop at
-    srv.py:238-244 sets out to do, and tested there with the same ``== 1.0`` rule (srv.py:262-263)."""
+    srv.py:238-244 sets out to do, and tested there with the same ``== 1.0`` rule (srv.py:262-263).
+
+    ``bilinear=True`` selects the OPT-IN mode NEOMPC_COSTMAP_BILINEAR — NOT the reference's
+    behaviour: the costmap term of srv.py:257-260 becomes (w_costmap c^2 + (1000 - w_costmap) l^2)/N with c and l the
+    bilinear interpolations of the cell cost and of the lethal indicator; equal to the reference's term at cell centres."""
     n_steps = params.control_steps
     dt = params.dt
     cost_total = 0
@@ -190,7 +194,10 @@ def objective(params: MpcParams, costmap, footprint_world, prob, cmd_vel, moving
         cost_total += params.w_control * (np.linalg.norm(
             np.array((v0x, v0y, v0z)) - np.array((vx, vy, om)))) / n_steps      # :253-254
 
-        if cell == 1.0:                                                        # :257
+        if bilinear:
+            cb, lb = costmap.bilinear_at_world(pos_x, pos_y)[:2]
+            cost_total += (params.w_costmap * float(cb) ** 2 + (1000 - params.w_costmap) * float(lb) ** 2) / n_steps
+        elif cell == 1.0:                                                      # :257
             cost_total += costmap_cost * 1000 / n_steps                        # :258
         else:
             cost_total += params.w_costmap * costmap_cost / n_steps            # :260
@@ -256,7 +263,8 @@ def make_bounds_and_constraints(params: MpcParams):
     return bnds, cons
 
 
-def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, maxiter=None, moving_footprint=None):
+def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, maxiter=None, moving_footprint=None,
+                bilinear=False):
     """Exactly the reference's call (srv.py:363-364): SLSQP, finite-difference gradients."""
     if x0 is None:
         x0 = np.zeros(params.control_steps * 3)                                # srv.py:136
@@ -264,7 +272,7 @@ def slsqp_solve(params: MpcParams, costmap, fp_world, prob, x0=None, ftol=None, 
     opts = {"ftol": params.opt_tolerance if ftol is None else ftol, "disp": False}
     if maxiter is not None:
         opts["maxiter"] = maxiter
-    fun = partial(objective, params, costmap, fp_world, prob, moving_footprint=moving_footprint)
+    fun = partial(objective, params, costmap, fp_world, prob, moving_footprint=moving_footprint, bilinear=bilinear)
     return minimize(fun, np.array(x0, dtype=np.float64), method="SLSQP",
                     bounds=bnds, constraints=cons, options=opts)
 
@@ -423,7 +431,7 @@ def moving_footprint_lethal(params: MpcParams, costmap, reqs, U, footprint_robot
     return out
 
 
-def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None, moving_footprint=None):
+def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None, moving_footprint=None, bilinear=False):
     """Vectorised J for a batch (same formula as ``objective``).  ``fp_lethal``: bool[B], whether
     the current footprint cost == 1.0 (None -> all False).  ``costmap`` may be None (free space).
     ``moving_footprint``: robot-frame polygon -> the opt-in moving-footprint mode (then fp_lethal is ignored)."""
@@ -437,7 +445,10 @@ def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None, moving_
     J = ((p.w_trans * d2 + p.w_orient * oe ** 2) / n).sum(axis=1)
     v0 = np.stack([_col(reqs, "vel_x"), _col(reqs, "vel_y"), _col(reqs, "vel_theta")], axis=1)
     J += (p.w_control * np.sqrt(((v0[:, None, :] - U) ** 2).sum(axis=2)) / n).sum(axis=1)
-    if costmap is not None:
+    if costmap is not None and bilinear:
+        c, l = costmap.bilinear_at_world(px, py)[:2]
+        J += ((p.w_costmap * c ** 2 + (1000.0 - p.w_costmap) * l ** 2) / n).sum(axis=1)
+    elif costmap is not None:
         c = costmap.cost_at_world(px, py)
         J += (np.where(c == 1.0, 1000.0, p.w_costmap) * c ** 2 / n).sum(axis=1)
     if moving_footprint is not None and costmap is not None:
@@ -450,9 +461,10 @@ def objective_batch(params: MpcParams, costmap, reqs, U, fp_lethal=None, moving_
     return J
 
 
-def gradient_batch(params: MpcParams, reqs, U, eps_control=0.0):
+def gradient_batch(params: MpcParams, reqs, U, eps_control=0.0, bilinear_costmap=None):
     """Analytic gradient of the smooth part of J (costmap / footprint terms are piecewise
-    constant -> 0 a.e.).  Control term: (u - v0)/sqrt(|u - v0|^2 + eps^2), 0 at the kink."""
+    constant -> 0 a.e.).  Control term: (u - v0)/sqrt(|u - v0|^2 + eps^2), 0 at the kink.
+    ``bilinear_costmap``: a GridCostmap -> adds the gradient of the opt-in bilinear costmap term."""
     p = params
     n = p.control_steps
     dt = p.dt
@@ -468,6 +480,16 @@ def gradient_batch(params: MpcParams, reqs, U, eps_control=0.0):
     gy = -2.0 * p.w_trans * (cy - y) / n
     gz = -2.0 * p.w_orient * (_col(reqs, "carrot_yaw")[:, None] - z) / n
     gz[:, -1] += -2.0 * p.w_orient * p.w_terminal * (_col(reqs, "goal_yaw") - z[:, -1])
+    if bilinear_costmap is not None:
+        # world position = pose + R(yaw0) (x, y): d/dx = cos(yaw0) d/dwx + sin(yaw0) d/dwy, d/dy = -sin d/dwx + cos d/dwy
+        y0 = _col(reqs, "pose_yaw_objective")[:, None]
+        px = _col(reqs, "pose_x")[:, None] + np.cos(y0) * x - np.sin(y0) * y
+        py = _col(reqs, "pose_y")[:, None] + np.sin(y0) * x + np.cos(y0) * y
+        cb, lb, dcx, dcy, dlx, dly = bilinear_costmap.bilinear_at_world(px, py)
+        gwx = 2.0 * (p.w_costmap * cb * dcx + (1000.0 - p.w_costmap) * lb * dlx) / n
+        gwy = 2.0 * (p.w_costmap * cb * dcy + (1000.0 - p.w_costmap) * lb * dly) / n
+        gx = gx + np.cos(y0) * gwx + np.sin(y0) * gwy
+        gy = gy - np.sin(y0) * gwx + np.cos(y0) * gwy
     Sx = np.cumsum(gx[:, ::-1], axis=1)[:, ::-1]
     Sy = np.cumsum(gy[:, ::-1], axis=1)[:, ::-1]
     Gz = gz - Sx * dy + Sy * dx

@@ -29,6 +29,7 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.T.flag = e.tab.flag.data();
   e.c.cells = cells;
   e.c.lethal_byte = enc == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
+  e.c.cm_scale = 1.0f / (float)e.c.lethal_byte;
   e.c.W = W; e.c.H = H;
   e.c.inv_res = (float)(1.0 / res);
   e.c.inv_res_d = 1.0 / res;
@@ -48,14 +49,14 @@ template <int S>
 void solve_all(const Env& e, const neompc_request* reqs, size_t n, neompc_response* out, float* plan) {
   std::vector<float> hist((size_t)hist_floats_per_lane<S>(e.c.m));
   for (size_t i = 0; i < n; ++i)
-    solve_instance<1, S>(e.c, e.T, reqs[i], true, 0, hist.data(), 1, &out[i], nullptr,
+    solve_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, hist.data(), 1, &out[i], nullptr,
                          plan ? plan + i * 3 * e.c.N : nullptr);
 }
 
 template <int S>
 void eval_all(const Env& e, const neompc_request* reqs, const float* u, size_t n, float* J, float* g) {
   for (size_t i = 0; i < n; ++i)
-    eval_instance<1, S>(e.c, e.T, reqs[i], true, 0, u + i * 3 * e.c.N, &J[i], g ? g + i * 3 * e.c.N : nullptr);
+    eval_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, u + i * 3 * e.c.N, &J[i], g ? g + i * 3 * e.c.N : nullptr);
 }
 
 template <int S>

@@ -97,7 +97,7 @@ def test_tilings_agree(Solver):
     U = rng.uniform(-0.7, 0.7, (wl.batch, 30)).astype(np.float32)
     ref = None
     sols = {}
-    for lanes in (2, 4, 5, 6, 8, 10, 16, 32):
+    for lanes in (3, 4, 5, 6, 8, 10, 16, 32):
         with Solver(wl.params, lanes_per_instance=lanes) as s:
             s.load_workload(wl)
             assert s.tiling[0] == lanes
