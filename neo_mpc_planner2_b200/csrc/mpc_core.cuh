@@ -80,7 +80,6 @@ struct SolverConst {
   float pair_eps;      // curvature pairs with s.y <= pair_eps * y.y are skipped
   float pin_alpha;     // an accepted arc parameter this small counts likewise (kPinnedAlpha)
   float tol_x;         // an accepted step shorter than this (sup norm) counts as "the objective stopped moving"
-  int precond;         // 1: block-diagonal initial inverse Hessian in the two-loop recursion (Solver::precondition); 0: gamma I
   // costmap (Costmap2d, srv.py:118)
   const uint8_t* cells;   // device pointer or nullptr (free space)
   int W, H;
@@ -297,9 +296,11 @@ inline Vec2 project_general(const SolverConst& P, float vx, float vy) {
   return Vec2{ox, oy};
 }
 
+// X = false: the caller guarantees P.disc_only (the general case analysis is not even compiled in)
+template <bool X>
 NEOMPC_HD void project_step(const SolverConst& P, float& vx, float& vy, float& om) {
   om = clampf(om, P.lo[2], P.hi[2]);
-  if (P.disc_only) {                                   // radial scaling, branch-free
+  if (!X || P.disc_only) {                             // radial scaling, branch-free
     const float n2 = vx * vx + vy * vy;
     const float sc = fminf(1.0f, P.R * rsqrt_f(fmaxf(n2, 1e-30f)));
     vx *= sc;
@@ -354,8 +355,10 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
   return c;
 }
 
-// X = true compiles the opt-in objective extensions (moving footprint, bilinear costmap) in; the reference-mode
-// kernels are instantiated with X = false so that their hot loop carries none of that code (it cost 7-20 % there).
+// X = true is the general build: opt-in objective extensions (moving footprint, bilinear costmap), the general
+// box-and-disc projection and the accurate sincosf.  X = false is the reference fast path — no extension, disc inside the
+// box (P.disc_only), heading range within MUFU accuracy (P.fast_trig); the dispatcher picks it only when all three hold —
+// so that its hot loop carries none of the other code (merely being present cost 7-20 % there).
 template <int G, int S, bool X>
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
@@ -495,7 +498,7 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       z[j] += zoff;
-      sincos_heading(P.fast_trig != 0, z[j], &s[j], &c[j]);
+      sincos_heading(!X || P.fast_trig != 0, z[j], &s[j], &c[j]);
       dx[j] = (u[j][0] * c[j] - u[j][1] * s[j]) * dt;                              // srv.py:231
       dy[j] = (u[j][0] * s[j] + u[j][1] * c[j]) * dt;                              // srv.py:232
       ax += dx[j]; x[j] = ax;
@@ -671,13 +674,13 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
 template <int S>
 NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2) + 2 * S; }   // pairs + (av, aw) of precondition()
 
-template <int S>
+template <int S, bool X>
 NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
   float pgmax = 0.0f;
   NEOMPC_UNROLL
   for (int j = 0; j < S; ++j) {
     float a = u[j][0] - g[j][0], b = u[j][1] - g[j][1], w = u[j][2] - g[j][2];
-    project_step(P, a, b, w);
+    project_step<X>(P, a, b, w);
     pg[j][0] = u[j][0] - a; pg[j][1] = u[j][1] - b; pg[j][2] = u[j][2] - w;
     pgmax = fmaxf(pgmax, fmaxf(fabsf(pg[j][0]), fmaxf(fabsf(pg[j][1]), fabsf(pg[j][2]))));
   }
@@ -709,7 +712,7 @@ struct Solver {
   bool fp_hit, has_instance;
   // iterate
   float u[S][3], g[S][3], pg[S][3];
-  float f, pgmax, gamma;
+  float f, pgmax;
   unsigned iters, evals, status;
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
@@ -752,7 +755,7 @@ struct Solver {
       u[j][0] = ld ? row[3 * i + 0] : 0.0f;          // warm start (srv.py:397-400) or zeros (srv.py:136,359)
       u[j][1] = ld ? row[3 * i + 1] : 0.0f;
       u[j][2] = ld ? row[3 * i + 2] : 0.0f;
-      project_step(P, u[j][0], u[j][1], u[j][2]);
+      project_step<X>(P, u[j][0], u[j][1], u[j][2]);
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
     }
@@ -769,7 +772,7 @@ struct Solver {
         tab[(size_t)(2 * j + 1) * stride] = dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N);
       }
     }
-    f = 0.0f; pgmax = 0.0f; gamma = 1.0f;
+    f = 0.0f; pgmax = 0.0f;
     iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
     hist_len = 0; head = 0; small_steps = 0;
     active = valid; force_pg = true; plain = false; first = true;
@@ -831,14 +834,8 @@ struct Solver {
       NEOMPC_UNROLL
       for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] -= a * yp[(size_t)e * stride];
     }
-    const bool use_pc = P.precond != 0 && !plain;
-    const float h0 = P.precond ? 1.0f : (use_qn ? gamma : 1.0f);
-    if (P.precond) {
-      precondition(P, hist, stride, use_pc, r);
-    } else {
-      NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) { r[j][0] *= h0; r[j][1] *= h0; r[j][2] *= h0; }
-    }
+    const bool use_pc = !plain;                    // initial matrix of the recursion: the block-diagonal preconditioner
+    precondition(P, hist, stride, use_pc, r);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -868,11 +865,11 @@ struct Solver {
     }
     gd = Grp<G>::sum(gd);
     pgn2 = Grp<G>::sum(pgn2);
-    const bool qn_dir = (use_qn || use_pc) && (gd < -1e-4f * pgn2 * h0);
+    const bool qn_dir = (use_qn || use_pc) && (gd < -1e-4f * pgn2);
     // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
     // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
     // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
-    if (P.disc_only) {
+    if (!X || P.disc_only) {
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) {
         const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
@@ -908,7 +905,7 @@ struct Solver {
         xt[j][0] = u[j][0] + alpha * d[j][0];
         xt[j][1] = u[j][1] + alpha * d[j][1];
         xt[j][2] = u[j][2] + alpha * d[j][2];
-        project_step(P, xt[j][0], xt[j][1], xt[j][2]);
+        project_step<X>(P, xt[j][0], xt[j][1], xt[j][2]);
         gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
       }
       gs = Grp<G>::sum(gs);
@@ -938,7 +935,7 @@ struct Solver {
     // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
     float gn[S][3], pgn[S][3];
     fw.backward(P, I, xt, lg, gn);
-    const float pgmax_n = Grp<G>::max(projected_gradient<S>(P, xt, gn, pgn));
+    const float pgmax_n = Grp<G>::max(projected_gradient<S, X>(P, xt, gn, pgn));
     // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
     // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
     float sy = 0.0f, yy = 0.0f, smax = 0.0f;
@@ -963,7 +960,6 @@ struct Solver {
             sp[(size_t)(3 * S + e) * stride] = r[e / 3][e % 3];
           }
           sp[(size_t)(6 * S) * stride] = div_approx(1.0f, sy);
-          gamma = div_approx(sy, yy);
           head = head + 1 == m ? 0 : head + 1;
           hist_len = hist_len < m ? hist_len + 1 : m;
           force_pg = false;

@@ -112,7 +112,6 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.tol_pg = kPgScale * p.opt_tolerance;
   c.tol_f = kFScale * p.opt_tolerance;
   c.tol_x = kXScale * p.opt_tolerance;
-  c.precond = 1;
   c.pin_alpha = kPinnedAlpha;
   c.pair_eps = 1e-10f;
   c.cells = nullptr;

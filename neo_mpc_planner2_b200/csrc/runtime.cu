@@ -152,7 +152,9 @@ constexpr unsigned kLatencyBatch = 32;
 cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   const bool latency = !eval && a.n <= kLatencyBatch;
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
-  const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST;
+  // general build unless the reference fast path applies (see Forward in mpc_core.cuh)
+  const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST ||
+                   !h->c.disc_only || !h->c.fast_trig;
   switch (G) {
     case 1: return launch_g1(eval, S, ext, a);
     case 2: return launch_g2(eval, S, ext, a);

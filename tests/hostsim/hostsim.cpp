@@ -39,7 +39,6 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.c.state = state;
   e.c.state_rows = state_rows;
   if (getenv("HOSTSIM_PAIREPS")) e.c.pair_eps = atof(getenv("HOSTSIM_PAIREPS"));
-  if (getenv("HOSTSIM_PRECOND")) e.c.precond = atoi(getenv("HOSTSIM_PRECOND"));
   if (getenv("HOSTSIM_TOLX")) { e.c.tol_x = atof(getenv("HOSTSIM_TOLX")); e.c.pin_alpha = 0.0f; }
   if (tol_pg > 0) e.c.tol_pg = tol_pg;
   if (tol_f >= 0) e.c.tol_f = tol_f;
@@ -107,7 +106,7 @@ int hostsim_state_stride(int n_steps) { return state_stride_for(n_steps); }
 void hostsim_project(const neompc_params* p, float* v, size_t n) {
   SolverConst c;
   build_const(*p, c);
-  for (size_t i = 0; i < n; ++i) project_step(c, v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  for (size_t i = 0; i < n; ++i) project_step<true>(c, v[3 * i], v[3 * i + 1], v[3 * i + 2]);
 }
 
 }  // extern "C"
