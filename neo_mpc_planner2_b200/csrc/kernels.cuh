@@ -82,8 +82,16 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 #ifndef NEOMPC_MINBLOCKS_S2
 #define NEOMPC_MINBLOCKS_S2 5
 #endif
+// NEOMPC_MINBLOCKS_RAW_S3: resident blocks of kBlockThreads (64) per SM the S = 3 kernels are compiled for, unscaled.
+// 7 instead of 8: ptxas still allocates 128 registers (8 blocks stay resident) but schedules differently — measured
+// C3 0.3965 -> 0.3926 ms, C4 1.488 -> 1.420 ms; 9 blocks (96 registers, 408 B of spills): 0.518 / 1.694 ms
+// (profiles/minblocks_sweep_r1.txt).
+#ifndef NEOMPC_MINBLOCKS_RAW_S3
+#define NEOMPC_MINBLOCKS_RAW_S3 7
+#endif
 // resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
 constexpr int min_blocks_for(int S) {
+  if (S == 3 && kBlockThreads == 64) return NEOMPC_MINBLOCKS_RAW_S3;
   return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : 3) * (128 / kBlockThreads);
 }
 
