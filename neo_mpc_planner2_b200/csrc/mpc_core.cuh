@@ -759,9 +759,10 @@ struct Solver {
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
     }
-    for (int e = 0; e < P.m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
+    const int m = X ? P.m : 1;                     // the fast path is dispatched only for one history pair
+    for (int e = 0; e < m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
     {
-      float* tab = hist + (size_t)(P.m * PAIR) * stride;             // tracking-term majorants of precondition()
+      float* tab = hist + (size_t)(m * PAIR) * stride;               // tracking-term majorants of precondition()
       const float dt2 = 2.0f * P.dt * P.dt;
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) {
@@ -788,7 +789,7 @@ struct Solver {
   //   aw = 2 (w_orient/N) dt^2 rowsum_i + 2 w_orient w_terminal dt^2 N.
   // The 3x3 block is inverted in closed form (Sherman-Morrison).  `on` = false leaves r unchanged (predicated).
   NEOMPC_HD void precondition(const SolverConst& P, const float* hist, int stride, bool on, float (*r)[3]) const {
-    const float* tab = hist + (size_t)(P.m * PAIR) * stride;         // (av_j, aw_j) written by init()
+    const float* tab = hist + (size_t)((X ? P.m : 1) * PAIR) * stride;   // (av_j, aw_j) written by init()
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
@@ -809,7 +810,7 @@ struct Solver {
 
   // one iteration for every group of the warp (inactive groups compute and discard)
   NEOMPC_HD void pass(const SolverConst& P, const CostTables& T, float* hist, int stride, int lg) {
-    const int m = P.m;
+    const int m = X ? P.m : 1;                     // compile-time 1 on the fast path: the two loops below unroll away
     Forward<G, S, X> fw;
     float d[S][3], xt[S][3], r[S][3];
 

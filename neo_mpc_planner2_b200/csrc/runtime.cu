@@ -154,7 +154,7 @@ cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
   // general build unless the reference fast path applies (see Forward in mpc_core.cuh)
   const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST ||
-                   !h->c.disc_only || !h->c.fast_trig;
+                   !h->c.disc_only || !h->c.fast_trig || h->c.m != 1;
   switch (G) {
     case 1: return launch_g1(eval, S, ext, a);
     case 2: return launch_g2(eval, S, ext, a);
