@@ -1,13 +1,13 @@
 // mpc_core.cuh — the per-instance MPC solve: rollout, cost, analytic gradient, projection onto box∩disc,
-// projected L-BFGS, and the optimizer() epilogue.  One *lane group* of G lanes (G = 1..32, a power of two,
-// G lanes of one warp) owns one MPC instance; each lane holds S consecutive control steps in registers
-// (G*S >= control_steps).  Cross-lane work (prefix/suffix scans of the rollout and its adjoint, dot products)
+// preconditioned projected L-BFGS, and the optimizer() epilogue.  One *lane group* of G lanes of one warp
+// (G = 1, 2, 3, 4, 5, 6, 8, 10, 16 or 32; 32/G groups per warp) owns one MPC instance; each lane holds S <= 4
+// consecutive control steps in registers (G*S >= control_steps).  Cross-lane work (prefix/suffix scans of the rollout and its adjoint, dot products)
 // is done with warp shuffles; all groups of a warp run in lock step.
 //
 // What it computes follows /root/reference/neo_mpc_planner2/mpc_optimization_server.py ("srv.py"):
 //   objective()            srv.py:204-269      -> Forward::run  (value)  + backward() (analytic gradient)
 //   f_constraint + bounds  srv.py:125-134,157  -> project_step  (exact projection onto box ∩ disc)
-//   minimize(SLSQP)        srv.py:363-364      -> solve_instance (projected L-BFGS; a different algorithm for the same NLP)
+//   minimize(SLSQP)        srv.py:363-364      -> Solver::pass (preconditioned projected L-BFGS; a different algorithm, same NLP)
 //   optimizer() epilogue   srv.py:358-361,366-402 -> solve_instance tail
 //   collision_check        srv.py:312-347
 //
@@ -692,15 +692,15 @@ NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], co
 //   prologue()  request -> per-instance constants, footprint cost, state row, start point   (srv.py:350-361)
 //   pass()      one iteration of the projected L-BFGS                                        (srv.py:363-364)
 //   epilogue()  low-pass, collision check, accel clamp, state, response                      (srv.py:366-402)
-// so that a kernel can either run one instance per group (solve_instance) or refill finished groups from a
-// work queue while the other groups of the warp keep iterating (solve_queue_kernel).
+// (one instance per group per launch: solve_instance below).
 //
 // Projected L-BFGS on the smoothed objective over the feasible set  prod_i (box ∩ disc):
-//   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion; pg = x - Proj(x - g) is the
-//   projected gradient; the secant pairs are those of the map pg, so an active disc constraint contributes
-//   its curvature), binding constraints frozen along the step, Armijo backtracking along the projection arc on
-//   the true objective incl. the piecewise-constant costmap term; falls back to a projected-gradient step when
-//   the quasi-Newton arc fails.  The first pass of an instance only evaluates its start point.
+//   x_{k+1} = Proj(x_k + alpha d_k),  d_k = -H_k pg_k  (two-loop recursion whose initial matrix is the block-diagonal
+//   preconditioner of precondition(); pg = x - Proj(x - g) is the projected gradient; the secant pairs are those of
+//   the map pg, so an active disc constraint contributes its curvature), binding constraints frozen along the step,
+//   Armijo backtracking along the projection arc on the true objective incl. the piecewise-constant costmap term;
+//   when an arc fails: history dropped -> preconditioned gradient -> plain projected gradient -> stop.
+//   The first pass of an instance only evaluates its start point.
 // Every collective (shuffle / vote) in here is executed by all 32 lanes of the warp; per-group decisions are
 // predicates, never branches around a collective.
 // ---------------------------------------------------------------------------------------------------------
