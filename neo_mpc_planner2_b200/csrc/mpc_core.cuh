@@ -647,8 +647,13 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
     const int sxs = ddx >= 0 ? 1 : -1, sys = ddy >= 0 ? 1 : -1;
     const bool xmaj = adx >= ady;
     const int den = xmaj ? adx : ady, numadd = xmaj ? ady : adx;
+    // floor((den/2 + k numadd) / den) without an integer division per pixel: (v + 0.5) / den is never within
+    // 0.5/den of an integer, far more than the float error for v < 2^20, so truncating the float product is exact
+    const float inv_den = den > 0 ? 1.0f / (float)den : 0.0f;
+    const bool small = den < 1024;
     for (int k = lg; k <= den; k += G) {
-      const int minor = den > 0 ? (den / 2 + k * numadd) / den : 0;
+      const int v = den / 2 + k * numadd;
+      const int minor = den <= 0 ? 0 : small ? (int)(((float)v + 0.5f) * inv_den) : v / den;
       const int cxp = xmaj ? mx0 + k * sxs : mx0 + minor * sxs;
       const int cyp = xmaj ? my0 + minor * sys : my0 + k * sys;
       int cell = kCellOob;
