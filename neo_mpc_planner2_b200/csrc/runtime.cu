@@ -144,13 +144,13 @@ int ensure_staging(neompc_handle* h, size_t n, bool want_plan, bool want_msgs) {
   return NEOMPC_OK;
 }
 
-// A handful of requests (a controller tick) cannot fill the device: what matters then is the length of the serial
-// instruction stream of one warp, which is shortest with one step per lane.  Measured for one request, N = 10:
-// (4,3) 69 us, (16,1) 58 us through neompc_solve_msgs (profiles/latency_n1_r1.txt).
-constexpr unsigned kLatencyBatch = 32;
-
+// A batch that cannot fill the device (a controller tick, a fleet of a few thousand robots) is limited by the length
+// of the serial instruction stream of one warp, not by throughput; that stream is shortest with one step per lane.
+// The latency tiling is used while all instances are resident at once with it (16 warps per SM).  Measured, N = 10:
+// one request (4,3) 69 us -> (16,1) 58 us through neompc_solve_msgs; 4096 requests: profiles/latency_n1_r1.txt.
 cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
-  const bool latency = !eval && a.n <= kLatencyBatch;
+  const size_t resident_lanes = (size_t)h->sm_count * 16u * 32u;
+  const bool latency = !eval && (size_t)a.n * (size_t)h->Gl <= resident_lanes;
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
   // general build unless the reference fast path applies (see Forward in mpc_core.cuh)
   const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST ||
