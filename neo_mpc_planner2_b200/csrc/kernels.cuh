@@ -29,6 +29,7 @@ struct LaunchArgs {
   float* J;                    // device [n]
   float* grad;                 // device [n*3N] or null
   cudaStream_t stream;
+  unsigned tiling_n;           // batch size the lane tiling is chosen for (0: n); the chunked host path passes the total
 };
 
 // thread -> (instance slot of the block, lane inside the group): 32/G groups per warp, leftover lanes idle

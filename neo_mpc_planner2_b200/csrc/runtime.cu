@@ -150,7 +150,8 @@ int ensure_staging(neompc_handle* h, size_t n, bool want_plan, bool want_msgs) {
 // one request (4,3) 69 us -> (16,1) 58 us through neompc_solve_msgs; 4096 requests: profiles/latency_n1_r1.txt.
 cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   const size_t resident_lanes = (size_t)h->sm_count * 16u * 32u;
-  const bool latency = !eval && (size_t)a.n * (size_t)h->Gl <= resident_lanes;
+  const size_t tn = a.tiling_n ? a.tiling_n : a.n;
+  const bool latency = !eval && tn * (size_t)h->Gl <= resident_lanes;
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
   // general build unless the reference fast path applies (see Forward in mpc_core.cuh)
   const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST ||
@@ -211,7 +212,7 @@ __global__ void reset_rows_kernel(float* state, int stride, const uint32_t* ids,
 }
 
 int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
-                    float* d_twist, float* d_plan, cudaStream_t s) {
+                    float* d_twist, float* d_plan, cudaStream_t s, size_t tiling_n = 0) {
   if (n == 0) return NEOMPC_OK;
   if (n > 0xFFFFFFF0ull) return fail(h, NEOMPC_ERR_INVALID, "batch too large");
   if ((reinterpret_cast<uintptr_t>(d_reqs) & 15u) != 0)      // the kernel stages request tiles with cp.async.bulk
@@ -226,6 +227,7 @@ int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, ne
   a.twist = d_twist;
   a.plan = d_plan;
   a.stream = s;
+  a.tiling_n = (unsigned)tiling_n;
   cudaError_t e = dispatch(h, false, a);
   if (e != cudaSuccess) return cuda_fail(h, e, "solve kernel launch");
   h->launches += 1;
@@ -494,7 +496,7 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
     const size_t cnt = n - lo < per ? n - lo : per;
     cudaStream_t s = streams[c & 1];
     NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs + lo, reqs + lo, cnt * sizeof(neompc_request), cudaMemcpyHostToDevice, s));
-    rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, nullptr, plan_or_null ? h->d_plan + lo * n3 : nullptr, s);
+    rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, nullptr, plan_or_null ? h->d_plan + lo * n3 : nullptr, s, n);
     if (rc != NEOMPC_OK) return rc;
     NEOMPC_CUDA(h, cudaMemcpyAsync(out + lo, h->d_resp + lo, cnt * sizeof(neompc_response), cudaMemcpyDeviceToHost, s));
     if (plan_or_null)

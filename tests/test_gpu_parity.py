@@ -275,12 +275,14 @@ def test_stateful_batch_is_tiling_invariant_in_layout(Solver):
         assert np.percentile(np.abs(costs[lanes] - costs[4]), 95) <= 2e-4
 
 
-def test_chunked_host_path_equals_device_path(Solver):
+@pytest.mark.parametrize("n_total", [40001, 17000])
+def test_chunked_host_path_equals_device_path(Solver, n_total):
     """neompc_solve_batch pipelines large batches in chunks over two streams; results must equal the single-launch
-    device path bit for bit."""
+    device path bit for bit (17000: each chunk alone would be small enough for the latency tiling — the lane tiling
+    must be chosen for the whole batch)."""
     import torch
     from neo_mpc_planner2_b200.abi import RESPONSE_DTYPE
-    wl, p, cm = setup_workload("c3", 40001, 10)
+    wl, p, cm = setup_workload("c3", n_total, 10)
     n = wl.batch
     with Solver(wl.params) as s:
         s.load_workload(wl)
