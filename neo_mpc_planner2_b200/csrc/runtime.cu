@@ -483,11 +483,14 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
     if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3s * sizeof(float));
     return NEOMPC_OK;
   }
-  // Large batches are cut into chunks that alternate between two streams, so the H2D copy of one chunk, the solve of
-  // another and the D2H copy of a third overlap (the copy engines for the two directions and the SMs are independent).
+  // Large batches are cut into two chunks on two streams, so the H2D copy of one chunk, the solve of
+  // the other and the D2H copies overlap (the copy engines for the two directions and the SMs are independent).
   // Problems are independent, so chunking does not change any result.
   const size_t n3 = 3 * (size_t)h->params.control_steps;
-  const int chunks = n >= 16384 ? 4 : 1;
+  static const int chunk_override = std::getenv("NEOMPC_CHUNKS") ? std::atoi(std::getenv("NEOMPC_CHUNKS")) : 0;   // tuning knob
+  // two chunks: as fast as four on a quiet host (0.452 vs 0.455 ms per 65536 requests) and much less sensitive to a busy
+  // one, where every extra enqueue costs (0.459 vs 0.596 ms; profiles/host_chunks_r1.txt)
+  const int chunks = n >= 16384 ? (chunk_override > 0 ? chunk_override : 2) : 1;
   const size_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
   cudaStream_t streams[2] = {h->stream, chunks > 1 ? h->stream2 : h->stream};
   for (int c = 0; c < chunks; ++c) {
