@@ -77,9 +77,6 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 }
 
 // resident blocks per SM the register allocator is asked to allow (65536 regs / (128 threads * blocks))
-#ifndef NEOMPC_MINBLOCKS_S3
-#define NEOMPC_MINBLOCKS_S3 4
-#endif
 #ifndef NEOMPC_MINBLOCKS_S2
 #define NEOMPC_MINBLOCKS_S2 5
 #endif
@@ -93,7 +90,7 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 // resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
 constexpr int min_blocks_for(int S) {
   if (S == 3 && kBlockThreads == 64) return NEOMPC_MINBLOCKS_RAW_S3;
-  return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? NEOMPC_MINBLOCKS_S3 : S == 1 ? 4 : 3) * (128 / kBlockThreads);
+  return (S == 2 ? NEOMPC_MINBLOCKS_S2 : S == 3 ? 4 : S == 1 ? 4 : 3) * (128 / kBlockThreads);
 }
 
 // ---- TMA (bulk async copy) staging of the block's request tile ------------------------------------------------

@@ -102,6 +102,11 @@ void hostsim_trace(int on) { g_trace = on; }
 
 int hostsim_state_stride(int n_steps) { return state_stride_for(n_steps); }
 
+// host logic of the dispatcher (mpc_setup.h): lane tiling for a horizon, throughput (latency = 0) or latency form
+void hostsim_choose_tiling(int n_steps, int lanes_override, int latency, int* G, int* S) {
+  if (latency) choose_latency_tiling(n_steps, G, S); else choose_tiling(n_steps, lanes_override, G, S);
+}
+
 // projection onto box ∩ disc, for property tests
 void hostsim_project(const neompc_params* p, float* v, size_t n) {
   SolverConst c;

@@ -124,3 +124,29 @@ def test_state_machine_sequences_on_host(golden):
             row = hs.state[1]
             assert np.abs(row[:n3] - osrv.initial_guess).max() <= 1e-6
             assert row[n3 + 3] == pytest.approx(osrv.waiting_time, abs=1e-5)
+
+
+def test_lane_tiling_choice():
+    """Host logic of the dispatcher (mpc_setup.h: choose_tiling / choose_latency_tiling): every horizon up to
+    NEOMPC_MAX_CONTROL_STEPS gets a tiling the library instantiates (S <= 4, G from the supported set, G*S >= N); the
+    auto choice reproduces the measured winners (profiles/tiling_sweep_r1c.txt, _r1d.txt)."""
+    import ctypes
+    from tests.hostsim import build
+    lib = ctypes.CDLL(build())
+    sizes = (1, 2, 3, 4, 5, 6, 8, 10, 16, 32)
+
+    def tiling(n, lanes=0, latency=0):
+        g, s = ctypes.c_int(), ctypes.c_int()
+        lib.hostsim_choose_tiling(n, lanes, latency, ctypes.byref(g), ctypes.byref(s))
+        return g.value, s.value
+    for n in range(1, 65):
+        for lat in (0, 1):
+            g, s = tiling(n, 0, lat)
+            assert g in sizes and 1 <= s <= 4 and g * s >= n and g * (s - 1) < n, (n, lat, g, s)
+        for lanes in sizes:
+            g, s = tiling(n, lanes)
+            assert g in sizes and g >= lanes and 1 <= s <= 4 and g * s >= n, (n, lanes, g, s)
+            if (n + lanes - 1) // lanes <= 4:
+                assert g == lanes
+    assert tiling(3) == (1, 3) and tiling(10) == (4, 3) and tiling(20) == (8, 3)
+    assert tiling(10, latency=1) == (16, 1) and tiling(3, latency=1) == (4, 1) and tiling(64, latency=1) == (32, 2)
