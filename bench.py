@@ -65,6 +65,20 @@ def _cpu_solve(i):
     return i, float(res.fun), res.x.astype(np.float64)
 
 
+def _cpu_solve_tight(i):
+    """The same problem converged tightly (ftol 1e-10, best of a cold start and a start from the ftol = opt_tolerance
+    point): the yardstick for 'how far is a first control from the optimum' (untimed; only with --dump-ref)."""
+    oracle, wl, p, cm = _W["oracle"], _W["wl"], _W["p"], _W["cm"]
+    from oracle.mpc_oracle import footprint_world
+    prob = oracle.Problem.from_record(wl.requests[i])
+    fpw = footprint_world(wl.footprint, prob.pose_x, prob.pose_y, prob.pose_yaw)
+    res = oracle.slsqp_solve(p, cm, fpw, prob)
+    a = oracle.slsqp_solve(p, cm, fpw, prob, x0=res.x, ftol=1e-10, maxiter=400)
+    b = oracle.slsqp_solve(p, cm, fpw, prob, ftol=1e-10, maxiter=400)
+    best = a if a.fun <= b.fun else b
+    return i, float(best.fun), best.x.astype(np.float64)
+
+
 def cpu_reference_rate(cfg, sample, cores, repeats=1):
     """solves/s of the reference algorithm on `sample` problems of the workload with `cores` processes."""
     import multiprocessing as mp
@@ -98,8 +112,10 @@ def run_reference(args):
         for _ in range(args.steps):
             last = pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
         dt = time.perf_counter() - t0
+        tight = pool.map(_cpu_solve_tight, range(min(sample, 4 * cores))) if args.dump_ref else None   # untimed
     if args.dump_ref and last:
-        np.savez(args.dump_ref, J=np.array([r[1] for r in last]), x=np.stack([r[2] for r in last]))
+        np.savez(args.dump_ref, J=np.array([r[1] for r in last]), x=np.stack([r[2] for r in last]),
+                 J_tight=np.array([r[1] for r in tight]), x_tight=np.stack([r[2] for r in tight]))
     value = args.steps * sample / dt
     wl_name, n_steps = _workload_name(args.config)
     line = {
@@ -407,6 +423,20 @@ def run_ours(args):
                     "max": float(dJ.max()), "frac_worse_than_1e-4": float((dJ > 1e-4).mean()),
                     "first_control_abs_diff_median": float(np.median(du)),
                     "first_control_abs_diff_p90": float(np.percentile(du, 90))}
+                if "x_tight" in refd:
+                    # the same comparison against the tightly converged reference optimum (ftol 1e-10): separates the
+                    # solver's own error from scipy's early stop at ftol = opt_tolerance
+                    kt = len(refd["J_tight"])
+                    dut = np.abs(plan[:kt, :3].astype(np.float64) - refd["x_tight"][:, :3]).max(axis=1)
+                    dus = np.abs(refd["x"][:kt, :3] - refd["x_tight"][:, :3]).max(axis=1)
+                    line["cost_residual"].update({
+                        "tight_problems": int(kt),
+                        "J_gpu_minus_J_scipy_tight_median": float(np.median(Jg[:kt] - refd["J_tight"])),
+                        "J_gpu_minus_J_scipy_tight_max": float((Jg[:kt] - refd["J_tight"]).max()),
+                        "first_control_vs_tight_scipy_median": float(np.median(dut)),
+                        "first_control_vs_tight_scipy_p90": float(np.percentile(dut, 90)),
+                        "scipy_at_opt_tolerance_vs_tight_scipy_median": float(np.median(dus)),
+                        "scipy_at_opt_tolerance_vs_tight_scipy_p90": float(np.percentile(dus, 90))})
             except Exception as exc:  # keep the GPU numbers even if the CPU arm failed
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"reference arm failed: {exc}: {res.stderr[-300:]}"}
