@@ -44,18 +44,34 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   if (tol_f >= 0) e.c.tol_f = tol_f;
 }
 
+// The same rule as the library's dispatcher (runtime.cu: dispatch): the reference fast path (X = false) when no
+// objective extension is on, the disc lies inside the box, headings stay in MUFU range and there is one history pair;
+// HOSTSIM_GENERAL=1 forces the general build so that both instantiations can be compared.
+bool fast_path(const Env& e) {
+  if (getenv("HOSTSIM_GENERAL")) return false;
+  return e.c.fp_mode == NEOMPC_FOOTPRINT_STATIC && e.c.cm_mode == NEOMPC_COSTMAP_NEAREST && e.c.disc_only &&
+         e.c.fast_trig && e.c.m == 1;
+}
+
 template <int S>
 void solve_all(const Env& e, const neompc_request* reqs, size_t n, neompc_response* out, float* plan) {
   std::vector<float> hist((size_t)hist_floats_per_lane<S>(e.c.m));
-  for (size_t i = 0; i < n; ++i)
-    solve_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, hist.data(), 1, &out[i], nullptr,
-                         plan ? plan + i * 3 * e.c.N : nullptr);
+  const bool fast = fast_path(e);
+  for (size_t i = 0; i < n; ++i) {
+    float* pl = plan ? plan + i * 3 * e.c.N : nullptr;
+    if (fast) solve_instance<1, S, false>(e.c, e.T, reqs[i], true, 0, hist.data(), 1, &out[i], nullptr, pl);
+    else solve_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, hist.data(), 1, &out[i], nullptr, pl);
+  }
 }
 
 template <int S>
 void eval_all(const Env& e, const neompc_request* reqs, const float* u, size_t n, float* J, float* g) {
-  for (size_t i = 0; i < n; ++i)
-    eval_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, u + i * 3 * e.c.N, &J[i], g ? g + i * 3 * e.c.N : nullptr);
+  const bool fast = fast_path(e);
+  for (size_t i = 0; i < n; ++i) {
+    float* gi = g ? g + i * 3 * e.c.N : nullptr;
+    if (fast) eval_instance<1, S, false>(e.c, e.T, reqs[i], true, 0, u + i * 3 * e.c.N, &J[i], gi);
+    else eval_instance<1, S, true>(e.c, e.T, reqs[i], true, 0, u + i * 3 * e.c.N, &J[i], gi);
+  }
 }
 
 template <int S>

@@ -150,3 +150,24 @@ def test_lane_tiling_choice():
                 assert g == lanes
     assert tiling(3) == (1, 3) and tiling(10) == (4, 3) and tiling(20) == (8, 3)
     assert tiling(10, latency=1) == (16, 1) and tiling(3, latency=1) == (4, 1) and tiling(64, latency=1) == (32, 2)
+
+
+def test_fast_path_and_general_build_agree(monkeypatch):
+    """The library instantiates the solver twice: the reference fast path (X = false: disc inside the box, MUFU-range
+    headings, one history pair, no objective extension, all folded at compile time) and the general build.  On a
+    workload that qualifies for the fast path both must compute the same thing (host build: bit-identical)."""
+    wl, p, cm = setup_workload("c3", 192, 10)
+    rng = np.random.default_rng(8)
+    U = rng.uniform(-0.7, 0.7, (wl.batch, 30)).astype(np.float32)
+    res = {}
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("HOSTSIM_GENERAL", "1")
+        else:
+            monkeypatch.delenv("HOSTSIM_GENERAL", raising=False)
+        hs = _hs(wl)
+        res[general] = (hs.eval(wl.requests, U), hs.solve(wl.requests))
+    (Ja, Ga), (oa, pa) = res[False]
+    (Jb, Gb), (ob, pb) = res[True]
+    assert Ja.tobytes() == Jb.tobytes() and Ga.tobytes() == Gb.tobytes()
+    assert pa.tobytes() == pb.tobytes() and oa.tobytes() == ob.tobytes()
