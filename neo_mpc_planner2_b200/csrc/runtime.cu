@@ -28,6 +28,7 @@ struct neompc_handle {
   int encoding = NEOMPC_ENC_OCCUPANCY;
   int G = 1, S = 1;         // lane-group tiling of batches (throughput)
   int Gl = 1, Sl = 1;       // tiling of tiny batches (latency): one step per lane where possible
+  bool force_general = false;   // NEOMPC_FORCE_GENERAL=1: always the general kernel build (test knob)
   float* d_lut_cost = nullptr;
   uint8_t* d_lut_flag = nullptr;
   uint8_t* d_cells = nullptr;
@@ -155,7 +156,7 @@ cudaError_t dispatch(neompc_handle* h, bool eval, const LaunchArgs& a) {
   const int G = latency ? h->Gl : h->G, S = latency ? h->Sl : h->S;
   // general build unless the reference fast path applies (see Forward in mpc_core.cuh)
   const bool ext = h->params.footprint_mode != NEOMPC_FOOTPRINT_STATIC || h->params.costmap_mode != NEOMPC_COSTMAP_NEAREST ||
-                   !h->c.disc_only || !h->c.fast_trig || h->c.m != 1;
+                   !h->c.disc_only || !h->c.fast_trig || h->c.m != 1 || h->force_general;
   switch (G) {
     case 1: return launch_g1(eval, S, ext, a);
     case 2: return launch_g2(eval, S, ext, a);
@@ -270,6 +271,7 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   if (!h) return fail(nullptr, NEOMPC_ERR_INVALID, "out of host memory");
   h->device = device;
   h->params = *params;
+  h->force_general = std::getenv("NEOMPC_FORCE_GENERAL") != nullptr;
 #define CREATE_CUDA(call)                                                                   \
   do {                                                                                      \
     cudaError_t e__ = (call);                                                               \

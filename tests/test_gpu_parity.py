@@ -275,6 +275,32 @@ def test_stateful_batch_is_tiling_invariant_in_layout(Solver):
         assert np.percentile(np.abs(costs[lanes] - costs[4]), 95) <= 2e-4
 
 
+def test_fast_path_kernel_agrees_with_general_kernel(Solver, monkeypatch):
+    """solve_kernel<G,S,false> (reference fast path, what the README parameters dispatch to) against
+    solve_kernel<G,S,true> (general build, forced with NEOMPC_FORCE_GENERAL) on the same batch: same objective values,
+    same solutions up to the reordering freedom the compiler has between two instantiations."""
+    wl, p, cm = setup_workload("c3", 4096 * 5, 10)
+    rng = np.random.default_rng(12)
+    U = rng.uniform(-0.7, 0.7, (wl.batch, 30)).astype(np.float32)
+    res = {}
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("NEOMPC_FORCE_GENERAL", "1")
+        else:
+            monkeypatch.delenv("NEOMPC_FORCE_GENERAL", raising=False)
+        with Solver(wl.params) as s:
+            s.load_workload(wl)
+            res[general] = (s.eval_objective(wl.requests, U), s.solve(wl.requests, want_plan=True))
+    (Ja, Ga), (oa, pa) = res[False]
+    (Jb, Gb), (ob, pb) = res[True]
+    assert np.abs(Ja - Jb).max() <= 2e-6 * max(1.0, np.abs(Ja).max()) and np.abs(Ga - Gb).max() <= 1e-6
+    fpl = footprint_lethal_flags(wl, cm, wl.requests[:2048])
+    Jfa = oracle.objective_batch(p, cm, wl.requests[:2048], pa[:2048].astype(np.float64), fp_lethal=fpl)
+    Jfb = oracle.objective_batch(p, cm, wl.requests[:2048], pb[:2048].astype(np.float64), fp_lethal=fpl)
+    assert np.percentile(np.abs(Jfa - Jfb), 99) <= 2e-4
+    assert abs(float(oa["iters"].mean()) - float(ob["iters"].mean())) <= 0.2
+
+
 @pytest.mark.parametrize("n_total", [40001, 17000])
 def test_chunked_host_path_equals_device_path(Solver, n_total):
     """neompc_solve_batch pipelines large batches in chunks over two streams; results must equal the single-launch
