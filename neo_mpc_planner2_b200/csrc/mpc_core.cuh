@@ -774,8 +774,12 @@ struct Solver {
         const int i = lg * S + j;
         const int rem = P.N - i > 0 ? P.N - i : 1;                   // padded steps: any positive value
         const float rowsum = (float)(rem * (i + 1) + ((rem - 1) * rem) / 2);
-        tab[(size_t)(2 * j) * stride] = dt2 * P.a_trans * rowsum;
-        tab[(size_t)(2 * j + 1) * stride] = dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N);
+        // Floors: with w_control = 0 and w_trans = 0 (or w_orient = 0) a block would be singular.  Without an
+        // orientation weight the heading still has curvature through the positions it swings (~ av * lever^2, lever
+        // up to max_vel_trans * horizon): 5 % of av stands in for that.
+        const float av = fmaxf(dt2 * P.a_trans * rowsum, 1e-12f);
+        tab[(size_t)(2 * j) * stride] = av;
+        tab[(size_t)(2 * j + 1) * stride] = fmaxf(dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N), 0.05f * av);
       }
     }
     f = 0.0f; pgmax = 0.0f;

@@ -171,3 +171,20 @@ def test_fast_path_and_general_build_agree(monkeypatch):
     (Jb, Gb), (ob, pb) = res[True]
     assert Ja.tobytes() == Jb.tobytes() and Ga.tobytes() == Gb.tobytes()
     assert pa.tobytes() == pb.tobytes() and oa.tobytes() == ob.tobytes()
+
+
+@pytest.mark.parametrize("over", [dict(w_control=0.0, w_orient=0.0), dict(w_control=0.0, w_trans=0.0),
+                                  dict(w_control=0.0, w_trans=0.0, w_orient=0.0, w_terminal=0.0),
+                                  dict(w_costmap=0.0, w_control=0.0)])
+def test_degenerate_weights(over):
+    """Zero weights make blocks of the preconditioner's model Hessian vanish; the solve must stay finite, feasible and
+    cheap (no runaway line searches) — a parameter file may well switch terms off."""
+    wl, p, cm = setup_workload("c3", 128, 10, **over)
+    out, plan = _hs(wl).solve(wl.requests)
+    assert np.isfinite(plan).all() and np.isfinite(out["cost"]).all()
+    assert feasibility_violation(wl.params, plan) <= 1e-6
+    assert (out["status"] != 1).all() and out["evals"].mean() <= 30
+    fpl = footprint_lethal_flags(wl, cm)
+    J0 = oracle.objective_batch(p, cm, wl.requests, np.zeros_like(plan, dtype=np.float64), fp_lethal=fpl)
+    Jg = oracle.objective_batch(p, cm, wl.requests, plan.astype(np.float64), fp_lethal=fpl)
+    assert (Jg <= J0 + 1e-5).all()
