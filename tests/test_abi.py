@@ -26,6 +26,35 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_header_is_plain_c():
+    """include/neompc.h is the drop-in boundary: it must compile as C99 (cgo / ctypes / plain C callers) and as C++."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "neompc.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    # and a C caller links against the library using nothing but the header
+    src = os.path.join(ROOT, "tests", "c_caller.c")
+    exe = os.path.join(ROOT, "tests", "hostsim", "_build", "c_caller")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", libdir, "-lneompc", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_caller_solves_on_gpu():
+    """The same plain-C program on a box with a GPU: creates a handle, solves the known-answer problem, rolls the path."""
+    import subprocess
+    test_header_is_plain_c()                       # builds tests/hostsim/_build/c_caller
+    out = subprocess.run([os.path.join(ROOT, "tests", "hostsim", "_build", "c_caller")], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi ok (twist 0.0833" in out.stdout, out.stdout + out.stderr
+
+
 def test_record_sizes(lib):
     sz = (ctypes.c_size_t * 7)()
     assert lib.neompc_abi_sizes(sz) == 0
