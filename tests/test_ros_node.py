@@ -58,6 +58,24 @@ def test_node_module_mirrors_reference_interface(ros):
     assert issubclass(ros_node.MpcOptimizationServer, ros.Node)
 
 
+def test_dynamic_parameter_semantics_match_the_reference(ros):
+    """tests/golden/dynamic_params_golden.json records, from the UNMODIFIED reference, which of the 14 names its
+    cb_params accepts (srv.py:405-439) actually change the objective, the constraint or the optimizer's result: the
+    bounds are built once (srv.py:125-133) and w_costmap / w_footprint are copied at start-up (srv.py:96-97).  The node
+    shim must treat exactly that set as effective in its reference-faithful mode."""
+    import json
+    from neo_mpc_planner2_b200 import ros_node
+    with open(os.path.join(HERE, "golden", "dynamic_params_golden.json")) as f:
+        facts = json.load(f)["facts"]
+    names = [k for k in facts if not k.startswith("_")]
+    assert set(names) == set(ros_node.DYNAMIC_NAMES)
+    effective = {k for k in names if facts[k]["objective_changed"] or facts[k]["constraint_changed"] or facts[k]["result_changed"]}
+    assert effective == set(ros_node.EFFECTIVE_IN_REFERENCE)
+    for k in names:                     # no parameter changes the result without changing objective or constraint
+        assert facts[k]["result_changed"] == (facts[k]["objective_changed"] or facts[k]["constraint_changed"])
+    assert facts["_non_double_ignored"] is True
+
+
 @pytest.mark.gpu
 def test_node_answers_like_the_library(ros):
     from neo_mpc_planner2_b200 import ros_node
