@@ -38,7 +38,7 @@ NEW = dict(min_vel_x=-0.2, min_vel_y=-0.2, min_vel_trans=-0.2, min_vel_theta=-0.
 PROB = dict(vel_x=0.1, vel_y=-0.05, vel_theta=0.2, carrot_x=0.4, carrot_y=0.1, carrot_yaw=0.3, goal_x=3.0, goal_y=1.0,
             goal_yaw=0.5, pose_x=0.5, pose_y=0.5, pose_yaw=0.2, control_interval=1.0 / 30.0, delta_t=1.0 / 30.0)
 # scenario B starts from rest and has a whole second of acceleration headroom, so the accel clamp (srv.py:385-391)
-# does not hide differences between solutions (with this scipy version SLSQP stalls at the zero start when v0 != 0)
+# does not hide differences between solutions (for scenario A's input this scipy version returns the zero start unchanged)
 PROB_B = dict(PROB, vel_x=0.0, vel_y=0.0, vel_theta=0.0, control_interval=1.0)
 
 
