@@ -403,12 +403,12 @@ int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances) {
   const int stride = state_stride_for(h->params.control_steps);
   float* fresh = nullptr;
   NEOMPC_CUDA(h, cudaMalloc(&fresh, (size_t)n_instances * stride * sizeof(float)));
-  NEOMPC_CUDA(h, cudaMemsetAsync(fresh, 0, (size_t)n_instances * stride * sizeof(float), h->stream));
-  if (h->d_state) {
-    NEOMPC_CUDA(h, cudaMemcpyAsync(fresh, h->d_state, (size_t)h->state_rows * stride * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, h->stream));
-  }
-  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaError_t e = cudaMemsetAsync(fresh, 0, (size_t)n_instances * stride * sizeof(float), h->stream);
+  if (e == cudaSuccess && h->d_state)
+    e = cudaMemcpyAsync(fresh, h->d_state, (size_t)h->state_rows * stride * sizeof(float), cudaMemcpyDeviceToDevice,
+                        h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { cudaFree(fresh); return cuda_fail(h, e, "reserve_instances"); }
   if (h->d_state) cudaFree(h->d_state);
   h->d_state = fresh;
   h->state_rows = n_instances;
@@ -428,10 +428,12 @@ int neompc_reset_state(neompc_handle* h, const uint32_t* ids, size_t n) {
   } else if (n > 0) {
     uint32_t* d_ids = nullptr;
     NEOMPC_CUDA(h, cudaMalloc(&d_ids, n * sizeof(uint32_t)));
-    NEOMPC_CUDA(h, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    reset_rows_kernel<<<(unsigned)n, 64, 0, h->stream>>>(h->d_state, stride, d_ids, (unsigned)n, h->state_rows);
-    h->launches += 1;
-    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaError_t e = cudaMemcpyAsync(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      reset_rows_kernel<<<(unsigned)n, 64, 0, h->stream>>>(h->d_state, stride, d_ids, (unsigned)n, h->state_rows);
+      h->launches += 1;
+      e = cudaStreamSynchronize(h->stream);
+    }
     cudaFree(d_ids);
     if (e != cudaSuccess) return cuda_fail(h, e, "reset_state");
     return NEOMPC_OK;
