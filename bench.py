@@ -124,7 +124,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "control_steps": n_steps, "opt_tolerance": 1e-3,
                    "solver": "scipy SLSQP, finite-difference gradients (oracle port of srv.py:363-364)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "per_core": value / cores,
                          "sample": f"first {sample} problems of the workload per step, cold start, "
                                    f"multiprocessing.Pool({cores})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
