@@ -26,3 +26,33 @@ def test_reference_arm_other_ranks_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                          capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/bench_r1_c3_1gpu.json is a line bench.py printed on the B200 box: it must carry every key of the
+    measurement contract (task statement section 4 and the base bench contract)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "bench_r1_c3_1gpu.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "mpc_solves_per_sec" and d["unit"] == "solves/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "solves/s" and c["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "solves/s" and e["h2d_bytes_per_step"] == 64 * d["config"]["batch_per_gpu"]
+    assert e["d2h_bytes_per_step"] == 32 * d["config"]["batch_per_gpu"]
+    assert e["value"] < d["value"]                       # copies are inside the e2e region
+    assert d["gpu_launches"] == d["steps"]               # one solve kernel per timed step
+    k = d["clocks"]
+    assert k["sm_mhz"] and k["sm_max_mhz"] and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["cost_residual"]["median"] <= 0.0 and d["cost_residual"]["max"] <= 5e-3
