@@ -85,7 +85,8 @@ typedef struct neompc_params {
   int32_t control_steps;                                           /* srv.py:75; 1..NEOMPC_MAX_CONTROL_STEPS */
   int32_t max_iterations;      /* L-BFGS iteration cap (default 100 = SLSQP's maxiter default) */
   int32_t lbfgs_memory;        /* history pairs, 1..8 (default 3) */
-  float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254); default 1e-2 */
+  float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254);
+                                  default: 10 * opt_tolerance clamped to [1e-3, 1e-2] */
   int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
   int32_t footprint_mode;      /* NEOMPC_FOOTPRINT_* ; 0 = the reference's behaviour */
   int32_t costmap_mode;        /* NEOMPC_COSTMAP_* ; 0 = the reference's behaviour */

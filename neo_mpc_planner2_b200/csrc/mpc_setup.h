@@ -100,7 +100,11 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.cm_scale = 1.0f / 100.0f;                     // likewise updated with the encoding
   c.cm_w = p.w_costmap / (float)N;
   c.cm_wl = (1000.0f - p.w_costmap) / (float)N;
-  const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f) : 1e-2f;
+  // default smoothing length of the control-term kink: 10 x opt_tolerance within [1e-3, 1e-2] m/s — 1e-2 at the README's
+  // opt_tolerance = 1e-3; 1e-3 at the code default 1e-5, where w_control = 0.5 makes the 1e-2 bias (<= w_control eps / N per
+  // kinked step) visible against a tightly converged scipy (profiles/solver_tuning_r1.txt)
+  const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f)
+                                               : fminf(1e-2f, fmaxf(1e-3f, 10.0f * p.opt_tolerance));
   c.eps2 = eps * eps;
   c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;
   c.hi[0] = p.max_vel_x; c.hi[1] = p.max_vel_y; c.hi[2] = p.max_vel_theta;

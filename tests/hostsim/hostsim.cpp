@@ -38,6 +38,7 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   for (int i = 0; i < fp_n && i < NEOMPC_MAX_FOOTPRINT_VERTICES; ++i) { e.c.fp_x[i] = fp_xy[2 * i]; e.c.fp_y[i] = fp_xy[2 * i + 1]; }
   e.c.state = state;
   e.c.state_rows = state_rows;
+  if (getenv("HOSTSIM_PINALPHA")) e.c.pin_alpha = atof(getenv("HOSTSIM_PINALPHA"));
   if (getenv("HOSTSIM_PAIREPS")) e.c.pair_eps = atof(getenv("HOSTSIM_PAIREPS"));
   if (getenv("HOSTSIM_TOLX")) { e.c.tol_x = atof(getenv("HOSTSIM_TOLX")); e.c.pin_alpha = 0.0f; }
   if (tol_pg > 0) e.c.tol_pg = tol_pg;
