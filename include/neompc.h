@@ -51,6 +51,16 @@ enum {
   NEOMPC_COSTMAP_BILINEAR = 1
 };
 
+/* neompc_params.costmap_guidance: the reference's costmap term is piecewise constant (srv.py:246-247, 257-260), so a
+ * gradient-based solver cannot see an inflation slope and stops wherever a cost step blocks its path.  With guidance ON a
+ * solve first minimises J with the costmap term interpolated between cell centres (whose gradient bends the plan down the
+ * inflation slope), then continues from that point on the reference's objective until it converges there.  OFF solves on
+ * the reference's objective from the start (the round-1 behaviour; kept for A/B measurements). */
+enum {
+  NEOMPC_GUIDANCE_ON = 0,
+  NEOMPC_GUIDANCE_OFF = 1
+};
+
 /* error codes */
 enum {
   NEOMPC_OK = 0,
@@ -90,7 +100,9 @@ typedef struct neompc_params {
   int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
   int32_t footprint_mode;      /* NEOMPC_FOOTPRINT_* ; 0 = the reference's behaviour */
   int32_t costmap_mode;        /* NEOMPC_COSTMAP_* ; 0 = the reference's behaviour */
-  int32_t reserved[4];
+  int32_t costmap_guidance;    /* NEOMPC_GUIDANCE_* ; 0 = on.  Solver strategy only: the objective, and with it every reported
+                                  cost, stays the reference's (see DESIGN.md "Costmap guidance") */
+  int32_t reserved[3];
 } neompc_params;
 
 /*

@@ -83,6 +83,10 @@ FOOTPRINT_MOVING = 1          # opt-in: polygon placed at every predicted pose (
 COSTMAP_NEAREST = 0           # the reference: cost of the cell under the predicted position
 COSTMAP_BILINEAR = 1          # opt-in: bilinear interpolation between cell centres, gradient enters the solver (row N4)
 
+# neompc_params.costmap_guidance (solver strategy; the objective stays the reference's)
+GUIDANCE_ON = 0
+GUIDANCE_OFF = 1
+
 # neompc_params — the reference's 22 server parameters (srv.py:49-75) + solver knobs
 PARAMS_FIELDS = [
     ("acc_x_limit", "<f4"), ("acc_y_limit", "<f4"), ("acc_theta_limit", "<f4"),
@@ -100,7 +104,8 @@ PARAMS_FIELDS = [
     ("lanes_per_instance", "<i4"),
     ("footprint_mode", "<i4"),
     ("costmap_mode", "<i4"),
-    ("reserved", "<i4", (4,)),
+    ("costmap_guidance", "<i4"),
+    ("reserved", "<i4", (3,)),
 ]
 PARAMS_DTYPE = np.dtype(PARAMS_FIELDS, align=False)
 assert PARAMS_DTYPE.itemsize == 128

@@ -82,6 +82,10 @@ struct SolverConst {
   float tol_x;         // an accepted step shorter than this (sup norm) counts as "the objective stopped moving"
   // costmap (Costmap2d, srv.py:118)
   const uint8_t* cells;   // device pointer or nullptr (free space)
+  const uint32_t* cells4; // corner-packed copy of the costmap (corner_word() below) or nullptr; the hot loop reads this one
+  float skip_polish;      // guidance: no second phase when the staircase deviates less than this at the guided optimum
+  float cm_curv;          // curvature floor of the guided costmap term in the preconditioner (Solver::init)
+  int guided;             // 1: the solve starts on the interpolated costmap term (costmap guidance, Solver::sur)
   int W, H;
   float inv_res;
   double origin_x, origin_y, inv_res_d;
@@ -94,12 +98,33 @@ struct SolverConst {
   unsigned state_rows;
 };
 
-// tables derived from (encoding, w_costmap, N): lut_cost[b] = (c==1 ? 1000 : w_costmap) * c^2 / N  (srv.py:247,257-260)
+// tables derived from (encoding, w_costmap, N): lut_cost[b] = w_costmap * c^2 / N  (srv.py:247,260); a lethal cell
+// (c == 1.0) adds SolverConst::cm_wl = (1000 - w_costmap) / N on top (srv.py:257-258)
 // lut_flag[b]: bit0 c == 1.0 (lethal), bit1 c >= 0.99 (srv.py:338)
 struct CostTables {
   const float* cost;      // [kTableSize]  entry 256 = out-of-bounds (c = 1.0), entry 257 = no costmap (0)
   const uint8_t* flag;    // [kTableSize]
 };
+
+// Corner-packed costmap.  Entry (ix, iy), ix in [-2, W], iy in [-2, H], holds the bytes of the four cells
+// (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1) in bits 0-7, 8-15, 16-23, 24-31; a cell outside the map is stored as the
+// lethal byte (cost 1.0, DESIGN.md "Costmap semantics").  One aligned 32-bit load then serves both the reference's
+// nearest-cell term (srv.py:246-247: the cell containing the point is one of the four) and the interpolated term the
+// solver uses for guidance.  Row pitch W + 3; index (iy + 2) * (W + 3) + (ix + 2).
+constexpr int kCornerPad = 2;
+NEOMPC_HD int corner_pitch(int W) { return W + 3; }
+NEOMPC_HD size_t corner_words(int W, int H) { return (size_t)(W + 3) * (size_t)(H + 3); }
+NEOMPC_HD uint32_t corner_word(const uint8_t* cells, int W, int H, int lethal_byte, int ix, int iy) {
+  uint32_t w = 0;
+  NEOMPC_UNROLL
+  for (int q = 0; q < 4; ++q) {
+    const int cx = ix + (q & 1), cy = iy + (q >> 1);
+    const bool inb = (unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H;
+    const uint32_t b = inb ? (uint32_t)cells[(size_t)cy * W + cx] : (uint32_t)lethal_byte;
+    w |= b << (8 * q);
+  }
+  return w;
+}
 
 constexpr int kStateExtra = 12;   // floats after the 3N guess in a state row
 NEOMPC_HD int state_stride_for(int n_steps) { return 3 * n_steps + kStateExtra; }
@@ -362,6 +387,7 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
 template <int G, int S, bool X>
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
+  float cm_gap, cm_abs;  // guidance: this lane's sum of (interpolated - nearest-cell) costmap terms, signed and absolute
 
   // Table index of the cell under a base-frame offset (x, y) rotated by (cr, sr) from the current position:
   // 0..255 = the cell byte, kCellOob = outside the map, kCellFree = no costmap loaded.  Branch-free.
@@ -510,19 +536,51 @@ struct Forward {
     for (int j = 0; j < S; ++j) { x[j] += xoff; y[j] += yoff; }
   }
 
+  // Costmap sample at base-frame offset (x, y): the corner-packed word around the point and the interpolation
+  // weights.  Cell-centre coordinates relative to the base cell; entries are clamped to the padded range, where a
+  // point far outside the map sees four lethal corners.
+  static NEOMPC_HD uint32_t corner_at(const SolverConst& P, const Instance& I, float x, float y, float* tx, float* ty) {
+    const float gx = I.fx + (I.cq * x - I.sq * y) - 0.5f;
+    const float gy = I.fy + (I.sq * x + I.cq * y) - 0.5f;
+    const float flx = floorf(gx), fly = floorf(gy);
+    *tx = gx - flx;
+    *ty = gy - fly;
+    int ix = I.bx + (int)flx, iy = I.by + (int)fly;
+    ix = ix < -kCornerPad ? -kCornerPad : (ix > P.W ? P.W : ix);
+    iy = iy < -kCornerPad ? -kCornerPad : (iy > P.H ? P.H : iy);
+    const unsigned idx = (unsigned)(iy + kCornerPad) * (unsigned)corner_pitch(P.W) + (unsigned)(ix + kCornerPad);
+#if defined(__CUDA_ARCH__)
+    return __ldg(P.cells4 + idx);
+#else
+    return P.cells4[idx];
+#endif
+  }
+
   // This lane's share of J (srv.py:246-268) for the rollout held in the struct.  The control term uses
-  // sqrt(r^2 + eps^2); its reciprocal is kept for backward().
-  NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg) {
+  // sqrt(r^2 + eps^2); its reciprocal is kept for backward().  On return x[j], y[j] no longer hold the positions
+  // but the adjoint seeds dJ/dx_j, dJ/dy_j (tracking term + the costmap term where it has a gradient), which is all
+  // backward() needs of them.
+  // `sur` (per lane group): costmap guidance — the costmap term is the bilinear interpolation of the per-cell term
+  // table[cell] between the four surrounding cell centres (equal to the reference's term at every cell centre) and
+  // its gradient enters the seeds; otherwise the reference's term table[cell under the point] (gradient 0).
+  NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg,
+                       bool sur) {
     const bool bilinear = X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr;   // uniform
-    int cell[S];
-    NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j)                                                     // srv.py:246-247 via :234-236
-      cell[j] = bilinear ? kCellFree : cell_of(P, I, I.cq, I.sq, x[j], y[j]);       // (loads issued together)
+    const bool sampled = !bilinear && P.cells4 != nullptr;                                    // uniform
+    uint32_t word[S];
+    float tx[S], ty[S];
+    if (sampled) {
+      NEOMPC_UNROLL
+      for (int j = 0; j < S; ++j) word[j] = corner_at(P, I, x[j], y[j], &tx[j], &ty[j]);     // (loads issued together)
+    }
     float J = 0.0f;
+    cm_gap = 0.0f; cm_abs = 0.0f;
+    float cmx[S], cmy[S];
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { cmx[j] = 0.0f; cmy[j] = 0.0f; }
     if (bilinear) {
       for (int j = 0; j < S; ++j) {
-        float ddx, ddy;
-        const float t = bilinear_term(P, I, x[j], y[j], &ddx, &ddy);
+        const float t = bilinear_term(P, I, x[j], y[j], &cmx[j], &cmy[j]);
         J += (lg * S + j < P.N) ? t : 0.0f;
       }
     }
@@ -535,27 +593,51 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
+      const bool on = i < P.N;
       const float ex = I.cx - x[j], ey = I.cy - y[j], eo = I.tyaw - z[j];
       float st = P.a_trans * (ex * ex + ey * ey) + P.b_orient * (eo * eo);          // srv.py:250-252
       const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
       const float r2 = fmaxf(rx * rx + ry * ry + rz * rz + P.eps2, 1e-24f);
       rinv[j] = rsqrt_f(r2);
       st += P.w_ctrl * (r2 * rinv[j]);                                              // srv.py:253-254 (smoothed)
-      st += T.cost[cell[j]];                                                        // srv.py:257-260
+      if (sampled) {                                                                // srv.py:246-247, 257-260
+        const uint32_t w = word[j];
+        const float k00 = T.cost[w & 0xffu], k10 = T.cost[(w >> 8) & 0xffu];        // w_costmap c^2 / N per corner
+        const float k01 = T.cost[(w >> 16) & 0xffu], k11 = T.cost[w >> 24];
+        const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;                          // the cell containing the point
+        const float near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
+        const uint32_t nb = (w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu;
+        // a lethal cell (cost == 1.0) weighs 1000 instead of w_costmap (srv.py:257-258): piecewise constant in both
+        // phases — the guidance follows the inflation slope, the wall stays where the reference has it
+        const float wall = nb == (uint32_t)P.lethal_byte ? P.cm_wl : 0.0f;
+        const float ax = k10 - k00, bx = k11 - k01;
+        const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
+        const float val = k0 + ty[j] * (k1 - k0);
+        const float ggx = ax + ty[j] * (bx - ax), ggy = k1 - k0;                     // per cell
+        st += (sur ? val : near) + wall;
+        const float gap = (sur && on) ? val - near : 0.0f;
+        cm_gap += gap; cm_abs += fabsf(gap);
+        cmx[j] = sur ? ggx * I.cq + ggy * I.sq : 0.0f;                              // gx = .. + cq x - sq y
+        cmy[j] = sur ? ggy * I.cq - ggx * I.sq : 0.0f;                              // gy = .. + sq x + cq y
+      }
       const float ef = I.fyaw - z[j];
       st += (i == P.N - 1) ? P.bt_term * (ef * ef) : 0.0f;                          // srv.py:267-268
-      J += (i < P.N) ? st : 0.0f;
+      J += on ? st : 0.0f;
+      x[j] = on ? -2.0f * P.a_trans * ex + cmx[j] : 0.0f;                           // adjoint seeds
+      y[j] = on ? -2.0f * P.a_trans * ey + cmy[j] : 0.0f;
     }
     return J;
   }
 
-  NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg) {
+  NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg,
+                      bool sur) {
     rollout(P, u, lg);
-    return cost(P, T, I, u, lg);
+    return cost(P, T, I, u, lg, sur);
   }
 
-  // Adjoint of run(): gradient of the smooth part of J w.r.t. this lane's controls.
-  // Derivation in DESIGN.md ("Analytic gradient"); costmap/footprint terms are piecewise constant -> 0.
+  // Adjoint of run(): gradient of J w.r.t. this lane's controls (of the reference's objective the smooth part: its
+  // costmap / footprint terms are piecewise constant; with guidance the interpolated costmap term contributes
+  // through the seeds).  Derivation in DESIGN.md ("Analytic gradient").
   NEOMPC_HD void backward(const SolverConst& P, const Instance& I, const float (*u)[3], int lg,
                           float (*g)[3]) const {
     const float dt = P.dt;
@@ -565,18 +647,10 @@ struct Forward {
     for (int j = S - 1; j >= 0; --j) {
       const int i = lg * S + j;
       const bool on = i < P.N;
-      gx[j] = on ? -2.0f * P.a_trans * (I.cx - x[j]) : 0.0f;
-      gy[j] = on ? -2.0f * P.a_trans * (I.cy - y[j]) : 0.0f;
-      if (X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr) {       // uniform; re-gathers 4 cells (L1 hits)
-        float ddx, ddy;
-        bilinear_term(P, I, x[j], y[j], &ddx, &ddy);
-        gx[j] += on ? ddx : 0.0f;
-        gy[j] += on ? ddy : 0.0f;
-      }
       gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
       gz[j] += (i == P.N - 1) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
-      sx += gx[j]; gx[j] = sx;                  // local inclusive suffix sums
-      sy += gy[j]; gy[j] = sy;
+      sx += x[j]; gx[j] = sx;                   // local inclusive suffix sums of the seeds left by cost()
+      sy += y[j]; gy[j] = sy;
     }
     const float sxoff = Grp<G>::excl_suffix(sx, lg);
     const float syoff = Grp<G>::excl_suffix(sy, lg);
@@ -721,6 +795,8 @@ struct Solver {
   unsigned iters, evals, status;
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
+  float gap_u, gapabs_u; // guidance: per-lane (interpolated - nearest) costmap sums at the current iterate u
+  bool sur;              // costmap guidance: this solve is still on the interpolated costmap term (phase 1 of 2)
 
   NEOMPC_HD void prologue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
                           float* hist, int stride) {
@@ -764,6 +840,7 @@ struct Solver {
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
     }
+    sur = P.guided != 0 && P.cells4 != nullptr && !(X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR);
     const int m = X ? P.m : 1;                     // the fast path is dispatched only for one history pair
     for (int e = 0; e < m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
     {
@@ -777,12 +854,15 @@ struct Solver {
         // Floors: with w_control = 0 and w_trans = 0 (or w_orient = 0) a block would be singular.  Without an
         // orientation weight the heading still has curvature through the positions it swings (~ av * lever^2, lever
         // up to max_vel_trans * horizon): 5 % of av stands in for that.
-        const float av = fmaxf(dt2 * P.a_trans * rowsum, 1e-12f);
+        // With guidance the interpolated costmap term bends over one cell by about its own size: a fraction of
+        // (w_costmap / N) / resolution^2 keeps the position block from vanishing when w_trans is (nearly) zero.
+        const float acm = sur ? P.cm_curv * P.cm_w * P.inv_res * P.inv_res : 0.0f;
+        const float av = fmaxf(dt2 * fmaxf(P.a_trans, acm) * rowsum, 1e-12f);
         tab[(size_t)(2 * j) * stride] = av;
         tab[(size_t)(2 * j + 1) * stride] = fmaxf(dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N), 0.05f * av);
       }
     }
-    f = 0.0f; pgmax = 0.0f;
+    f = 0.0f; pgmax = 0.0f; gap_u = 0.0f; gapabs_u = 0.0f;
     iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
     hist_len = 0; head = 0; small_steps = 0;
     active = valid; force_pg = true; plain = false; first = true;
@@ -919,7 +999,7 @@ struct Solver {
         gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
       }
       gs = Grp<G>::sum(gs);
-      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg));
+      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg, sur));
       NEOMPC_TRACE("   trial bt %d alpha %.4g gs %.4e df %.4e gd %.4e\n", bt, alpha, gs, ftrial - f, gd);
       if (!ls_done) {
         ++evals;
@@ -983,6 +1063,7 @@ struct Solver {
         }
         f = ft;
         pgmax = pgmax_n;
+        gap_u = fw.cm_gap; gapabs_u = fw.cm_abs;
         if (!first) {
           ++iters;
           // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
@@ -1006,6 +1087,21 @@ struct Solver {
       if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
     }
     first = false;
+    // Costmap guidance, end of the first phase: the guided solve has settled on the interpolated costmap term.  Where the
+    // staircase of the reference's term is within the tolerance of what was minimised (sum over the steps of
+    // |interpolated - cell| <= skip_polish * opt_tolerance) the point is final and f becomes the reference's objective
+    // there; otherwise the solve continues from the point on the reference's objective (the next pass re-evaluates it).
+    const float gsum = Grp<G>::sum(gap_u), gabs = Grp<G>::sum(gapabs_u);     // (collectives: executed by every lane)
+    if (sur && !active && has_instance && status != NEOMPC_STATUS_MAXITER) {
+      sur = false;
+      if (gabs <= P.skip_polish) {
+        f -= gsum;
+      } else {
+        active = true; first = true; force_pg = true; plain = false;
+        hist_len = 0; head = 0; small_steps = 0;
+        status = NEOMPC_STATUS_MAXITER;
+      }
+    }
   }
 
   // post-solve part of optimizer() (srv.py:365-402).  Executed by every lane of the warp (it contains collectives);
@@ -1143,7 +1239,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
     u[j][2] = ld ? uin[3 * i + 2] : 0.0f;
   }
   Forward<G, S, X> fw;
-  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg));
+  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg, false));
   const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + constant_cost(P, rq, fp_hit);
   fw.backward(P, I, u, lg, g);
   if (!valid) return;

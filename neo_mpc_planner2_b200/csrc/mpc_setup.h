@@ -22,17 +22,24 @@ inline double cell_cost(int encoding, int byte) {
   return (byte >= 0 && byte <= 254) ? byte / 254.0 : 0.0;
 }
 
-// lut_cost[b] = (c == 1.0 ? 1000 : w_costmap) * c^2 / N     (srv.py:247, 257-260)
+// lut_cost[b] = w_costmap * c^2 / N (srv.py:247, 260); lethal cells add (1000 - w_costmap) / N in the kernel (srv.py:257-258)
 inline void build_tables(const neompc_params& p, int encoding, HostTables& t) {
   t.cost.assign(kTableSize, 0.0f);          // entry kCellFree (no costmap) stays 0
   t.flag.assign(kTableSize, 0);
   for (int b = 0; b <= 256; ++b) {
     const double c = b == 256 ? 1.0 : cell_cost(encoding, b);
-    const double cc = c * c;
-    const double v = (c == 1.0) ? cc * 1000.0 / p.control_steps : (double)p.w_costmap * cc / p.control_steps;
-    t.cost[b] = (float)v;
+    t.cost[b] = (float)((double)p.w_costmap * c * c / p.control_steps);
     t.flag[b] = (uint8_t)((c == 1.0 ? 1 : 0) | (c >= 0.99 ? 2 : 0));
   }
+}
+
+// corner-packed copy of a host costmap (mpc_core.cuh: corner_word); the CUDA runtime builds the same on the device
+inline void build_corner_map(const uint8_t* cells, int W, int H, int lethal_byte, std::vector<uint32_t>& out) {
+  out.resize(corner_words(W, H));
+  const int pitch = corner_pitch(W);
+  for (int iy = -kCornerPad; iy <= H; ++iy)
+    for (int ix = -kCornerPad; ix <= W; ++ix)
+      out[(size_t)(iy + kCornerPad) * pitch + (ix + kCornerPad)] = corner_word(cells, W, H, lethal_byte, ix, iy);
 }
 
 inline bool validate_params(const neompc_params& p, std::string& err) {
@@ -63,6 +70,10 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
     err = "footprint_mode must be NEOMPC_FOOTPRINT_STATIC or NEOMPC_FOOTPRINT_MOVING";
     return false;
   }
+  if (p.costmap_guidance != NEOMPC_GUIDANCE_ON && p.costmap_guidance != NEOMPC_GUIDANCE_OFF) {
+    err = "costmap_guidance must be NEOMPC_GUIDANCE_ON or NEOMPC_GUIDANCE_OFF";
+    return false;
+  }
   if (!(p.opt_tolerance > 0.0f)) { err = "opt_tolerance must be > 0"; return false; }
   const int g = p.lanes_per_instance;
   if (!(g == 0 || g == 1 || g == 2 || g == 3 || g == 4 || g == 5 || g == 6 || g == 8 || g == 10 || g == 16 || g == 32)) {
@@ -78,6 +89,8 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
 constexpr float kPgScale = 0.1f;
 constexpr float kFScale = 2e-3f;
 constexpr float kXScale = 0.1f;
+constexpr float kCmCurvature = 0.02f;   // SolverConst::cm_curv
+constexpr float kSkipPolish = 1.0f;      // SolverConst::skip_polish in units of opt_tolerance
 
 inline void build_const(const neompc_params& p, SolverConst& c) {
   std::memset(&c, 0, sizeof(c));
@@ -100,11 +113,12 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.cm_scale = 1.0f / 100.0f;                     // likewise updated with the encoding
   c.cm_w = p.w_costmap / (float)N;
   c.cm_wl = (1000.0f - p.w_costmap) / (float)N;
-  // default smoothing length of the control-term kink: 10 x opt_tolerance within [1e-3, 1e-2] m/s — 1e-2 at the README's
-  // opt_tolerance = 1e-3; 1e-3 at the code default 1e-5, where w_control = 0.5 makes the 1e-2 bias (<= w_control eps / N per
-  // kinked step) visible against a tightly converged scipy (profiles/solver_tuning_r1.txt)
+  // default smoothing length of the control-term kink: 10 x opt_tolerance within [1e-4, 1e-2] m/s — 1e-2 at the README's
+  // opt_tolerance = 1e-3; 1e-4 at the code default 1e-5, where w_control = 0.5 makes the bias (<= w_control eps / N per
+  // kinked step) visible against a tightly converged scipy: 1e-3 left 8 % of free-space problems worse than scipy by
+  // more than 1e-4, 1e-4 none (profiles/solver_tuning_r2.txt)
   const float eps = p.control_smoothing > 0.0f ? fmaxf(p.control_smoothing, 1e-6f)
-                                               : fminf(1e-2f, fmaxf(1e-3f, 10.0f * p.opt_tolerance));
+                                               : fminf(1e-2f, fmaxf(1e-4f, 10.0f * p.opt_tolerance));
   c.eps2 = eps * eps;
   c.lo[0] = p.min_vel_x; c.lo[1] = p.min_vel_y; c.lo[2] = p.min_vel_theta;
   c.hi[0] = p.max_vel_x; c.hi[1] = p.max_vel_y; c.hi[2] = p.max_vel_theta;
@@ -116,9 +130,15 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.tol_pg = kPgScale * p.opt_tolerance;
   c.tol_f = kFScale * p.opt_tolerance;
   c.tol_x = kXScale * p.opt_tolerance;
-  c.pin_alpha = kPinnedAlpha;
+  // the pinned-arc stop trades accuracy for evaluations at a costmap cell edge: only at tolerances that ask for no more
+  // (at the code default 1e-5 it ended solves with a projected gradient of 0.1 still standing)
+  c.pin_alpha = p.opt_tolerance > 1e-4f ? kPinnedAlpha : 0.0f;
   c.pair_eps = 1e-10f;
   c.cells = nullptr;
+  c.cells4 = nullptr;
+  c.cm_curv = kCmCurvature;
+  c.skip_polish = kSkipPolish * p.opt_tolerance;
+  c.guided = (p.costmap_guidance == NEOMPC_GUIDANCE_ON && p.costmap_mode == NEOMPC_COSTMAP_NEAREST) ? 1 : 0;
   c.state = nullptr;
   c.state_stride = state_stride_for(N);
   c.state_rows = 0;

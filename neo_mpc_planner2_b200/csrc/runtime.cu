@@ -33,6 +33,8 @@ struct neompc_handle {
   uint8_t* d_lut_flag = nullptr;
   uint8_t* d_cells = nullptr;
   size_t cells_cap = 0;
+  uint32_t* d_cells4 = nullptr;    // corner-packed copy (mpc_core.cuh: corner_word), what the solve kernel samples
+  size_t cells4_cap = 0;
   float* d_state = nullptr;
   unsigned state_rows = 0;
   // staging for the host-buffer entry points
@@ -105,7 +107,7 @@ int upload_tables(neompc_handle* h) {
 void rebuild_const(neompc_handle* h) {
   const SolverConst old = h->c;
   build_const(h->params, h->c);
-  h->c.cells = old.cells; h->c.W = old.W; h->c.H = old.H;
+  h->c.cells = old.cells; h->c.cells4 = old.cells4; h->c.W = old.W; h->c.H = old.H;
   h->c.inv_res = old.inv_res; h->c.inv_res_d = old.inv_res_d;
   h->c.origin_x = old.origin_x; h->c.origin_y = old.origin_y;
   h->c.fp_n = old.fp_n;
@@ -202,6 +204,17 @@ __global__ void pack_kernel(const neompc_optimizer_request* __restrict__ msgs, u
   r.delta_t = (float)fmin(m.delta_t, 3.0e38);
   r.instance_id = m.instance_id;
   reqs[i] = r;
+}
+
+// corner-packed copy of the costmap: one thread per entry of the padded (W+3) x (H+3) grid
+__global__ void corner_map_kernel(const uint8_t* __restrict__ cells, int W, int H, int lethal_byte,
+                                  uint32_t* __restrict__ out) {
+  const int pitch = corner_pitch(W);
+  const size_t total = corner_words(W, H);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int iy = (int)(i / pitch) - kCornerPad, ix = (int)(i % pitch) - kCornerPad;
+    out[i] = corner_word(cells, W, H, lethal_byte, ix, iy);
+  }
 }
 
 __global__ void reset_rows_kernel(float* state, int stride, const uint32_t* ids, unsigned n, unsigned rows) {
@@ -306,7 +319,7 @@ int neompc_destroy(neompc_handle* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
-  cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_state);
+  cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_cells4); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
   cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan);
@@ -346,7 +359,7 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
   if (encoding != NEOMPC_ENC_OCCUPANCY && encoding != NEOMPC_ENC_NAV2_RAW)
     return fail(h, NEOMPC_ERR_INVALID, "unknown costmap encoding");
   if (cells == nullptr) {                      // free space
-    h->c.cells = nullptr; h->c.W = h->c.H = 0;
+    h->c.cells = nullptr; h->c.cells4 = nullptr; h->c.W = h->c.H = 0;
     return NEOMPC_OK;
   }
   if (width == 0 || height == 0 || width > 65535u || height > 65535u || !(resolution > 0.0))
@@ -359,20 +372,36 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
     NEOMPC_CUDA(h, cudaMalloc(&h->d_cells, bytes));
     h->cells_cap = bytes;
   }
+  const size_t words = corner_words((int)width, (int)height);
+  if (words > h->cells4_cap) {
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_cells4) cudaFree(h->d_cells4);
+    h->d_cells4 = nullptr; h->cells4_cap = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_cells4, words * sizeof(uint32_t)));
+    h->cells4_cap = words;
+  }
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_cells, cells, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                  h->stream));
   h->c.cells = h->d_cells;
+  h->c.cells4 = h->d_cells4;
   h->c.W = (int)width; h->c.H = (int)height;
   h->c.inv_res_d = 1.0 / resolution;
   h->c.inv_res = (float)(1.0 / resolution);
   h->c.origin_x = origin_x; h->c.origin_y = origin_y;
   h->resolution = resolution;
-  if (encoding != h->encoding) {
+  const bool enc_changed = encoding != h->encoding;
+  if (enc_changed) {
     h->encoding = encoding;
     h->c.lethal_byte = encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
     h->c.cm_scale = 1.0f / (float)h->c.lethal_byte;
-    return upload_tables(h);
   }
+  {
+    const unsigned blocks = (unsigned)((words + 255) / 256 < 4096 ? (words + 255) / 256 : 4096);
+    corner_map_kernel<<<blocks, 256, 0, h->stream>>>(h->d_cells, h->c.W, h->c.H, h->c.lethal_byte, h->d_cells4);
+    NEOMPC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+  }
+  if (enc_changed) return upload_tables(h);
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   return NEOMPC_OK;
 }

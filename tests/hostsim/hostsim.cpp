@@ -19,6 +19,7 @@ struct Env {
   SolverConst c;
   HostTables tab;
   CostTables T;
+  std::vector<uint32_t> cells4;
 };
 
 void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H, double res, double ox, double oy,
@@ -31,6 +32,10 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.c.lethal_byte = enc == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
   e.c.cm_scale = 1.0f / (float)e.c.lethal_byte;
   e.c.W = W; e.c.H = H;
+  if (cells != nullptr) {
+    build_corner_map(cells, W, H, e.c.lethal_byte, e.cells4);
+    e.c.cells4 = e.cells4.data();
+  }
   e.c.inv_res = (float)(1.0 / res);
   e.c.inv_res_d = 1.0 / res;
   e.c.origin_x = ox; e.c.origin_y = oy;
@@ -39,6 +44,8 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.c.state = state;
   e.c.state_rows = state_rows;
   if (getenv("HOSTSIM_PINALPHA")) e.c.pin_alpha = atof(getenv("HOSTSIM_PINALPHA"));
+  if (getenv("HOSTSIM_CMCURV")) e.c.cm_curv = atof(getenv("HOSTSIM_CMCURV"));
+  if (getenv("HOSTSIM_SKIPPOLISH")) e.c.skip_polish = atof(getenv("HOSTSIM_SKIPPOLISH")) * p->opt_tolerance;
   if (getenv("HOSTSIM_PAIREPS")) e.c.pair_eps = atof(getenv("HOSTSIM_PAIREPS"));
   if (getenv("HOSTSIM_TOLX")) { e.c.tol_x = atof(getenv("HOSTSIM_TOLX")); e.c.pin_alpha = 0.0f; }
   if (tol_pg > 0) e.c.tol_pg = tol_pg;
