@@ -215,7 +215,7 @@ def run_ours(args):
     n = wl.batch
     n_steps = wl.control_steps
     solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode,
-                         costmap_mode=args.costmap_mode)
+                         costmap_mode=args.costmap_mode, costmap_guidance=args.costmap_guidance)
     solver.load_workload(wl)
     G, S = solver.tiling
 
@@ -462,6 +462,9 @@ def main():
     ap.add_argument("--costmap-mode", type=int, default=0, choices=[0, 1],
                     help="0 = the reference's nearest-cell costmap term (default, parity mode); 1 = opt-in bilinear term "
                          "with gradient (SURVEY 8f row N4; no CPU baseline / cost residual for it)")
+    ap.add_argument("--costmap-guidance", type=int, default=0, choices=[0, 1],
+                    help="0 = costmap guidance on (default); 1 = off: solve on the reference's objective from the start "
+                         "(the round-1 strategy; A/B measurements)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ref", default="", help="reference arm: save per-problem J and x of the last pass (npz)")

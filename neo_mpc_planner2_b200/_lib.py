@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libneompc.so")
+# NEOMPC_LIB selects another build of the same library (tuning variants made by scripts/build_variant.sh)
+LIB_PATH = os.environ.get("NEOMPC_LIB") or os.path.join(HERE, "libneompc.so")
 
 # every symbol include/neompc.h declares
 EXPORTS = [

@@ -85,7 +85,7 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 // C3 0.3965 -> 0.3926 ms, C4 1.488 -> 1.420 ms; 9 blocks (96 registers, 408 B of spills): 0.518 / 1.694 ms
 // (profiles/minblocks_sweep_r1.txt).
 #ifndef NEOMPC_MINBLOCKS_RAW_S3
-#define NEOMPC_MINBLOCKS_RAW_S3 7
+#define NEOMPC_MINBLOCKS_RAW_S3 6
 #endif
 // resident 128-thread-equivalents per SM the register allocator must allow, scaled to the block size
 constexpr int min_blocks_for(int S) {

@@ -83,7 +83,10 @@ struct SolverConst {
   // costmap (Costmap2d, srv.py:118)
   const uint8_t* cells;   // device pointer or nullptr (free space)
   const uint32_t* cells4; // corner-packed copy of the costmap (corner_word() below) or nullptr; the hot loop reads this one
-  float skip_polish;      // guidance: no second phase when the staircase deviates less than this at the guided optimum
+  int pad4, pitch4;       // its padding and row pitch
+  int pad_ok;             // 1: the padding covers twice a plan's reach -> the solver samples without bounds tests
+  float k_lethal;         // lut_cost entry of the lethal byte (unique to it: build_tables)
+  float sur_tol;          // guidance: the first phase stops at sur_tol x the tolerances of the second
   float cm_curv;          // curvature floor of the guided costmap term in the preconditioner (Solver::init)
   int guided;             // 1: the solve starts on the interpolated costmap term (costmap guidance, Solver::sur)
   int W, H;
@@ -106,14 +109,16 @@ struct CostTables {
   const uint8_t* flag;    // [kTableSize]
 };
 
-// Corner-packed costmap.  Entry (ix, iy), ix in [-2, W], iy in [-2, H], holds the bytes of the four cells
-// (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1) in bits 0-7, 8-15, 16-23, 24-31; a cell outside the map is stored as the
-// lethal byte (cost 1.0, DESIGN.md "Costmap semantics").  One aligned 32-bit load then serves both the reference's
+// Corner-packed costmap.  Entry (ix, iy), ix in [-pad, W + pad), iy in [-pad, H + pad), holds the bytes of the four
+// cells (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1) in bits 0-7, 8-15, 16-23, 24-31; a cell outside the map is stored as
+// the lethal byte (cost 1.0, DESIGN.md "Costmap semantics").  One aligned 32-bit load then serves both the reference's
 // nearest-cell term (srv.py:246-247: the cell containing the point is one of the four) and the interpolated term the
-// solver uses for guidance.  Row pitch W + 3; index (iy + 2) * (W + 3) + (ix + 2).
-constexpr int kCornerPad = 2;
-NEOMPC_HD int corner_pitch(int W) { return W + 3; }
-NEOMPC_HD size_t corner_words(int W, int H) { return (size_t)(W + 3) * (size_t)(H + 3); }
+// solver uses for guidance.  `pad` is twice what a feasible plan can travel (max_vel_trans * prediction_horizon /
+// resolution cells) plus slack, corner_pad_for(): any start within reach of the map indexes exactly, without bounds tests
+// (make_instance).
+// Row pitch W + 2 pad; index (iy + pad) * pitch + (ix + pad).
+NEOMPC_HD int corner_pitch(int W, int pad) { return W + 2 * pad; }
+NEOMPC_HD size_t corner_words(int W, int H, int pad) { return (size_t)(W + 2 * pad) * (size_t)(H + 2 * pad); }
 NEOMPC_HD uint32_t corner_word(const uint8_t* cells, int W, int H, int lethal_byte, int ix, int iy) {
   uint32_t w = 0;
   NEOMPC_UNROLL
@@ -346,8 +351,36 @@ struct Instance {
   float v0x, v0y, v0z;   // current velocity                   (srv.py:216-218)
   float cq, sq;          // cos/sin of pose_yaw_objective / resolution  (srv.py:213, hoisted from :234-236)
   int bx, by;            // cell containing the current position
+  int base4;             // entry of that cell (clamped to the map's one-cell surround) in the corner-packed map
   float fx, fy;          // fractional position inside that cell, in cells
 };
+
+// srv.py:207-221 hoisted: everything objective() derives from the request alone
+NEOMPC_HD Instance make_instance(const SolverConst& P, const neompc_request& rq) {
+  Instance I;
+  I.cx = rq.carrot_x; I.cy = rq.carrot_y;
+  I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
+  I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
+  sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
+  I.sq *= P.inv_res; I.cq *= P.inv_res;
+  I.bx = I.by = 0; I.fx = I.fy = 0.0f; I.base4 = 0;
+  if (P.cells != nullptr) {
+    // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
+    const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
+    const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
+    const double bxd = fmin(fmax(floor(gx), -1.0e9), 1.0e9), byd = fmin(fmax(floor(gy), -1.0e9), 1.0e9);
+    I.bx = (int)bxd; I.by = (int)byd;
+    I.fx = (float)(gx - floor(gx)); I.fy = (float)(gy - floor(gy));
+    // Unchecked sampling indexes relative to the start cell.  A start more than a plan's reach outside the map sees lethal
+    // cells whatever it does, so it may stand in for any other such start: clamping it there keeps every index a
+    // feasible plan can produce inside the padded array (pad = 2 reach + 6, corner_pad_for).
+    const int reach = P.pad_ok ? (P.pad4 - 6) / 2 : 0;
+    const int bxc = I.bx < -(reach + 2) ? -(reach + 2) : (I.bx > P.W + reach + 1 ? P.W + reach + 1 : I.bx);
+    const int byc = I.by < -(reach + 2) ? -(reach + 2) : (I.by > P.H + reach + 1 ? P.H + reach + 1 : I.by);
+    I.base4 = (byc + P.pad4) * P.pitch4 + (bxc + P.pad4);
+  }
+  return I;
+}
 
 // terms of J that do not depend on u: terminal distance (srv.py:266) + footprint (srv.py:262-263)
 NEOMPC_HD float constant_cost(const SolverConst& P, const neompc_request& rq, bool fp_hit) {
@@ -387,7 +420,6 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
 template <int G, int S, bool X>
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
-  float cm_gap, cm_abs;  // guidance: this lane's sum of (interpolated - nearest-cell) costmap terms, signed and absolute
 
   // Table index of the cell under a base-frame offset (x, y) rotated by (cr, sr) from the current position:
   // 0..255 = the cell byte, kCellOob = outside the map, kCellFree = no costmap loaded.  Branch-free.
@@ -537,23 +569,31 @@ struct Forward {
   }
 
   // Costmap sample at base-frame offset (x, y): the corner-packed word around the point and the interpolation
-  // weights.  Cell-centre coordinates relative to the base cell; entries are clamped to the padded range, where a
-  // point far outside the map sees four lethal corners.
+  // weights (cell-centre coordinates relative to the start cell).  Checked = false: the caller guarantees a feasible
+  // plan, which cannot leave the padded map (corner_pad_for); Checked = true (test hook, arbitrary controls): a point
+  // outside the padded map sees four lethal corners.
+  template <bool Checked>
   static NEOMPC_HD uint32_t corner_at(const SolverConst& P, const Instance& I, float x, float y, float* tx, float* ty) {
     const float gx = I.fx + (I.cq * x - I.sq * y) - 0.5f;
     const float gy = I.fy + (I.sq * x + I.cq * y) - 0.5f;
     const float flx = floorf(gx), fly = floorf(gy);
     *tx = gx - flx;
     *ty = gy - fly;
-    int ix = I.bx + (int)flx, iy = I.by + (int)fly;
-    ix = ix < -kCornerPad ? -kCornerPad : (ix > P.W ? P.W : ix);
-    iy = iy < -kCornerPad ? -kCornerPad : (iy > P.H ? P.H : iy);
-    const unsigned idx = (unsigned)(iy + kCornerPad) * (unsigned)corner_pitch(P.W) + (unsigned)(ix + kCornerPad);
+    const int ox = (int)flx, oy = (int)fly;
+    bool inside = true;
+    int idx = I.base4 + oy * P.pitch4 + ox;
+    if (Checked || !P.pad_ok) {                  // absolute entry; anything outside the padded array is outside the map
+      const float lim = 1.0e9f;
+      const int ix = I.bx + (int)fminf(fmaxf(flx, -lim), lim), iy = I.by + (int)fminf(fmaxf(fly, -lim), lim);
+      inside = ix >= -P.pad4 && ix < P.W + P.pad4 && iy >= -P.pad4 && iy < P.H + P.pad4;
+      idx = inside ? (iy + P.pad4) * P.pitch4 + (ix + P.pad4) : 0;
+    }
 #if defined(__CUDA_ARCH__)
-    return __ldg(P.cells4 + idx);
+    const uint32_t w = __ldg(P.cells4 + idx);
 #else
-    return P.cells4[idx];
+    const uint32_t w = P.cells4[idx];
 #endif
+    return inside ? w : (uint32_t)P.lethal_byte * 0x01010101u;
   }
 
   // This lane's share of J (srv.py:246-268) for the rollout held in the struct.  The control term uses
@@ -563,6 +603,9 @@ struct Forward {
   // `sur` (per lane group): costmap guidance — the costmap term is the bilinear interpolation of the per-cell term
   // table[cell] between the four surrounding cell centres (equal to the reference's term at every cell centre) and
   // its gradient enters the seeds; otherwise the reference's term table[cell under the point] (gradient 0).
+  // A lethal cell (cost == 1.0) weighs 1000 instead of w_costmap (srv.py:257-258): that part stays piecewise constant
+  // in both cases — the guidance follows the inflation slope, the wall stays where the reference has it.
+  template <bool Checked>
   NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg,
                        bool sur) {
     const bool bilinear = X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr;   // uniform
@@ -571,10 +614,12 @@ struct Forward {
     float tx[S], ty[S];
     if (sampled) {
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) word[j] = corner_at(P, I, x[j], y[j], &tx[j], &ty[j]);     // (loads issued together)
+      for (int j = 0; j < S; ++j) word[j] = corner_at<Checked>(P, I, x[j], y[j], &tx[j], &ty[j]);   // (loads issued together)
     }
+    // the interpolation is skipped by warps none of whose groups is (still) guided
+    const bool any_sur = sampled && Grp<G>::warp_any(sur);                                    // warp-uniform
+    const float cqs = sur ? I.cq : 0.0f, sqs = sur ? I.sq : 0.0f, sf = sur ? 1.0f : 0.0f;
     float J = 0.0f;
-    cm_gap = 0.0f; cm_abs = 0.0f;
     float cmx[S], cmy[S];
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) { cmx[j] = 0.0f; cmy[j] = 0.0f; }
@@ -602,23 +647,24 @@ struct Forward {
       st += P.w_ctrl * (r2 * rinv[j]);                                              // srv.py:253-254 (smoothed)
       if (sampled) {                                                                // srv.py:246-247, 257-260
         const uint32_t w = word[j];
-        const float k00 = T.cost[w & 0xffu], k10 = T.cost[(w >> 8) & 0xffu];        // w_costmap c^2 / N per corner
-        const float k01 = T.cost[(w >> 16) & 0xffu], k11 = T.cost[w >> 24];
         const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;                          // the cell containing the point
-        const float near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
-        const uint32_t nb = (w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu;
-        // a lethal cell (cost == 1.0) weighs 1000 instead of w_costmap (srv.py:257-258): piecewise constant in both
-        // phases — the guidance follows the inflation slope, the wall stays where the reference has it
-        const float wall = nb == (uint32_t)P.lethal_byte ? P.cm_wl : 0.0f;
-        const float ax = k10 - k00, bx = k11 - k01;
-        const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
-        const float val = k0 + ty[j] * (k1 - k0);
-        const float ggx = ax + ty[j] * (bx - ax), ggy = k1 - k0;                     // per cell
-        st += (sur ? val : near) + wall;
-        const float gap = (sur && on) ? val - near : 0.0f;
-        cm_gap += gap; cm_abs += fabsf(gap);
-        cmx[j] = sur ? ggx * I.cq + ggy * I.sq : 0.0f;                              // gx = .. + cq x - sq y
-        cmy[j] = sur ? ggy * I.cq - ggx * I.sq : 0.0f;                              // gy = .. + sq x + cq y
+        float near;
+        if (any_sur) {
+          const float k00 = T.cost[w & 0xffu], k10 = T.cost[(w >> 8) & 0xffu];      // w_costmap c^2 / N per corner
+          const float k01 = T.cost[(w >> 16) & 0xffu], k11 = T.cost[w >> 24];
+          near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
+          const float ax = k10 - k00, bx = k11 - k01;
+          const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
+          const float val = k0 + ty[j] * (k1 - k0);
+          const float ggx = ax + ty[j] * (bx - ax), ggy = k1 - k0;                   // per cell
+          st += near + sf * (val - near);
+          cmx[j] = ggx * cqs + ggy * sqs;                                           // gx = .. + cq x - sq y
+          cmy[j] = ggy * cqs - ggx * sqs;                                           // gy = .. + sq x + cq y
+        } else {
+          near = T.cost[(w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu];
+          st += near;
+        }
+        st += near == P.k_lethal ? P.cm_wl : 0.0f;                                  // (the lethal entry is unique)
       }
       const float ef = I.fyaw - z[j];
       st += (i == P.N - 1) ? P.bt_term * (ef * ef) : 0.0f;                          // srv.py:267-268
@@ -629,10 +675,11 @@ struct Forward {
     return J;
   }
 
+  template <bool Checked>
   NEOMPC_HD float run(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg,
                       bool sur) {
     rollout(P, u, lg);
-    return cost(P, T, I, u, lg, sur);
+    return cost<Checked>(P, T, I, u, lg, sur);
   }
 
   // Adjoint of run(): gradient of J w.r.t. this lane's controls (of the reference's objective the smooth part: its
@@ -795,7 +842,6 @@ struct Solver {
   unsigned iters, evals, status;
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
-  float gap_u, gapabs_u; // guidance: per-lane (interpolated - nearest) costmap sums at the current iterate u
   bool sur;              // costmap guidance: this solve is still on the interpolated costmap term (phase 1 of 2)
 
   NEOMPC_HD void prologue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
@@ -809,20 +855,7 @@ struct Solver {
   NEOMPC_HD void init(const SolverConst& P, const neompc_request& rq, bool fp_any, bool valid, int lg,
                       float* hist, int stride) {
     has_instance = valid;
-    I.cx = rq.carrot_x; I.cy = rq.carrot_y;
-    I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
-    I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
-    sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
-    I.sq *= P.inv_res; I.cq *= P.inv_res;
-    I.bx = I.by = 0; I.fx = I.fy = 0.0f;
-    if (P.cells != nullptr) {
-      // nav2 worldToMap in float64, then a float32 offset inside the cell keeps sub-cell precision on big maps
-      const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
-      const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
-      const double bxd = floor(gx), byd = floor(gy);
-      I.bx = (int)bxd; I.by = (int)byd;
-      I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
-    }
+    I = make_instance(P, rq);
     fp_hit = valid && fp_any;
 
     // per-instance state and the new-goal reset (srv.py:358-361); the epilogue reads the row again
@@ -862,7 +895,7 @@ struct Solver {
         tab[(size_t)(2 * j + 1) * stride] = fmaxf(dt2 * (P.b_orient * rowsum + P.bt_term * (float)P.N), 0.05f * av);
       }
     }
-    f = 0.0f; pgmax = 0.0f; gap_u = 0.0f; gapabs_u = 0.0f;
+    f = 0.0f; pgmax = 0.0f;
     iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
     hist_len = 0; head = 0; small_steps = 0;
     active = valid; force_pg = true; plain = false; first = true;
@@ -999,7 +1032,7 @@ struct Solver {
         gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
       }
       gs = Grp<G>::sum(gs);
-      const float ftrial = Grp<G>::sum(fw.run(P, T, I, xt, lg, sur));
+      const float ftrial = Grp<G>::sum(fw.template run<false>(P, T, I, xt, lg, sur));
       NEOMPC_TRACE("   trial bt %d alpha %.4g gs %.4e df %.4e gd %.4e\n", bt, alpha, gs, ftrial - f, gd);
       if (!ls_done) {
         ++evals;
@@ -1063,12 +1096,12 @@ struct Solver {
         }
         f = ft;
         pgmax = pgmax_n;
-        gap_u = fw.cm_gap; gapabs_u = fw.cm_abs;
         if (!first) {
           ++iters;
           // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
           // (a step that short means the arc search is pinned at a costmap cell edge)
-          if (df <= P.tol_f * fmaxf(1.0f, fabsf(f)) || smax <= P.tol_x || alpha <= P.pin_alpha) ++small_steps;
+          const float ts = sur ? P.sur_tol : 1.0f;        // the guided phase is followed by a second one: looser stop
+          if (df <= ts * P.tol_f * fmaxf(1.0f, fabsf(f)) || smax <= ts * P.tol_x || alpha <= P.pin_alpha) ++small_steps;
           else small_steps = 0;
           if (small_steps >= 2) { active = false; status = NEOMPC_STATUS_CONVERGED; }
         }
@@ -1083,24 +1116,17 @@ struct Solver {
         status = NEOMPC_STATUS_LINESEARCH;
       }
       // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
-      if (active && pgmax <= P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
+      if (active && pgmax <= (sur ? P.sur_tol : 1.0f) * P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
       if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
     }
     first = false;
-    // Costmap guidance, end of the first phase: the guided solve has settled on the interpolated costmap term.  Where the
-    // staircase of the reference's term is within the tolerance of what was minimised (sum over the steps of
-    // |interpolated - cell| <= skip_polish * opt_tolerance) the point is final and f becomes the reference's objective
-    // there; otherwise the solve continues from the point on the reference's objective (the next pass re-evaluates it).
-    const float gsum = Grp<G>::sum(gap_u), gabs = Grp<G>::sum(gapabs_u);     // (collectives: executed by every lane)
+    // Costmap guidance, end of the first phase: the guided solve has settled on the interpolated costmap term; the solve
+    // continues from that point on the reference's objective (the next pass re-evaluates the point there).
     if (sur && !active && has_instance && status != NEOMPC_STATUS_MAXITER) {
       sur = false;
-      if (gabs <= P.skip_polish) {
-        f -= gsum;
-      } else {
-        active = true; first = true; force_pg = true; plain = false;
-        hist_len = 0; head = 0; small_steps = 0;
-        status = NEOMPC_STATUS_MAXITER;
-      }
+      active = true; first = true; force_pg = true; plain = false;
+      hist_len = 0; head = 0; small_steps = 0;
+      status = NEOMPC_STATUS_MAXITER;
     }
   }
 
@@ -1213,20 +1239,7 @@ NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const n
 template <int G, int S, bool X>
 NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
                              const float* uin, float* Jout, float* gout) {
-  Instance I;
-  I.cx = rq.carrot_x; I.cy = rq.carrot_y;
-  I.tyaw = rq.carrot_yaw; I.fyaw = rq.goal_yaw;
-  I.v0x = rq.vel_x; I.v0y = rq.vel_y; I.v0z = rq.vel_theta;
-  sincos_f(rq.pose_yaw_objective, &I.sq, &I.cq);
-  I.sq *= P.inv_res; I.cq *= P.inv_res;
-  I.bx = I.by = 0; I.fx = I.fy = 0.0f;
-  if (P.cells != nullptr) {
-    const double gx = ((double)rq.pose_x - P.origin_x) * P.inv_res_d;
-    const double gy = ((double)rq.pose_y - P.origin_y) * P.inv_res_d;
-    const double bxd = floor(gx), byd = floor(gy);
-    I.bx = (int)bxd; I.by = (int)byd;
-    I.fx = (float)(gx - bxd); I.fy = (float)(gy - byd);
-  }
+  const Instance I = make_instance(P, rq);
   const bool fp_any = footprint_lethal<G>(P, T, (double)rq.pose_x, (double)rq.pose_y, (double)rq.pose_yaw, lg);
   const bool fp_hit = valid && fp_any;
   float u[S][3], g[S][3];
@@ -1239,7 +1252,7 @@ NEOMPC_HD void eval_instance(const SolverConst& P, const CostTables& T, const ne
     u[j][2] = ld ? uin[3 * i + 2] : 0.0f;
   }
   Forward<G, S, X> fw;
-  const float f = Grp<G>::sum(fw.run(P, T, I, u, lg, false));
+  const float f = Grp<G>::sum(fw.template run<true>(P, T, I, u, lg, false));
   const float jt = f + unsmooth_correction<G, S>(P, I, u, lg) + constant_cost(P, rq, fp_hit);
   fw.backward(P, I, u, lg, g);
   if (!valid) return;

@@ -22,24 +22,41 @@ inline double cell_cost(int encoding, int byte) {
   return (byte >= 0 && byte <= 254) ? byte / 254.0 : 0.0;
 }
 
-// lut_cost[b] = w_costmap * c^2 / N (srv.py:247, 260); lethal cells add (1000 - w_costmap) / N in the kernel (srv.py:257-258)
+// lut_cost[b] = w_costmap * c^2 / N (srv.py:247, 260); lethal cells add (1000 - w_costmap) / N in the kernel (srv.py:257-258),
+// which recognises them by their table value: lethal_entry() is unique to c == 1.0 (1e-30 stands in when w_costmap = 0)
+inline float lethal_entry(const neompc_params& p) {
+  return fmaxf((float)((double)p.w_costmap / p.control_steps), 1e-30f);
+}
 inline void build_tables(const neompc_params& p, int encoding, HostTables& t) {
   t.cost.assign(kTableSize, 0.0f);          // entry kCellFree (no costmap) stays 0
   t.flag.assign(kTableSize, 0);
   for (int b = 0; b <= 256; ++b) {
     const double c = b == 256 ? 1.0 : cell_cost(encoding, b);
-    t.cost[b] = (float)((double)p.w_costmap * c * c / p.control_steps);
+    t.cost[b] = c == 1.0 ? lethal_entry(p) : (float)((double)p.w_costmap * c * c / p.control_steps);
     t.flag[b] = (uint8_t)((c == 1.0 ? 1 : 0) | (c >= 0.99 ? 2 : 0));
   }
 }
 
+// Padding of the corner-packed map: twice what a feasible plan can travel (the disc constraint bounds every step's speed
+// by max_vel_trans, srv.py:157-158) in cells — once for starts that lie outside the map but within reach of it, once for
+// the plan itself — plus the interpolation neighbour and slack (mpc_core.cuh: make_instance).
+// A reach of more than kMaxCornerReach cells (a very fine grid under a long horizon) would make the padded copy large:
+// the padding is capped and the solver samples with bounds tests instead (*pad_ok = 0).
+constexpr int kMaxCornerReach = 125;
+inline int corner_pad_for(const neompc_params& p, double resolution, int* pad_ok = nullptr) {
+  const double reach = std::ceil((double)p.max_vel_trans * (double)p.prediction_horizon / resolution);
+  const bool ok = reach <= (double)kMaxCornerReach;
+  if (pad_ok) *pad_ok = ok ? 1 : 0;
+  return ok ? 2 * (int)reach + 6 : 8;
+}
+
 // corner-packed copy of a host costmap (mpc_core.cuh: corner_word); the CUDA runtime builds the same on the device
-inline void build_corner_map(const uint8_t* cells, int W, int H, int lethal_byte, std::vector<uint32_t>& out) {
-  out.resize(corner_words(W, H));
-  const int pitch = corner_pitch(W);
-  for (int iy = -kCornerPad; iy <= H; ++iy)
-    for (int ix = -kCornerPad; ix <= W; ++ix)
-      out[(size_t)(iy + kCornerPad) * pitch + (ix + kCornerPad)] = corner_word(cells, W, H, lethal_byte, ix, iy);
+inline void build_corner_map(const uint8_t* cells, int W, int H, int lethal_byte, int pad, std::vector<uint32_t>& out) {
+  out.resize(corner_words(W, H, pad));
+  const int pitch = corner_pitch(W, pad);
+  for (int iy = -pad; iy < H + pad; ++iy)
+    for (int ix = -pad; ix < W + pad; ++ix)
+      out[(size_t)(iy + pad) * pitch + (ix + pad)] = corner_word(cells, W, H, lethal_byte, ix, iy);
 }
 
 inline bool validate_params(const neompc_params& p, std::string& err) {
@@ -86,11 +103,12 @@ inline bool validate_params(const neompc_params& p, std::string& err) {
 // Solver tolerances derived from the reference's opt_tolerance (SLSQP's ftol there).  See DESIGN.md
 // "Meaning of opt_tolerance": the projected-gradient sup-norm must fall below kPgScale * opt_tolerance, or the
 // objective must stop decreasing by more than kFScale * opt_tolerance (relative) twice in a row.
-constexpr float kPgScale = 0.1f;
-constexpr float kFScale = 2e-3f;
-constexpr float kXScale = 0.1f;
+constexpr float kPgScale = 0.2f;
+constexpr float kFScale = 4e-3f;
+constexpr float kXScale = 0.2f;
 constexpr float kCmCurvature = 0.02f;   // SolverConst::cm_curv
-constexpr float kSkipPolish = 1.0f;      // SolverConst::skip_polish in units of opt_tolerance
+constexpr float kGuidedTolScale = 2.0f;  // SolverConst::sur_tol
+      // SolverConst::skip_polish in units of opt_tolerance
 
 inline void build_const(const neompc_params& p, SolverConst& c) {
   std::memset(&c, 0, sizeof(c));
@@ -136,8 +154,10 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.pair_eps = 1e-10f;
   c.cells = nullptr;
   c.cells4 = nullptr;
+  c.pad4 = 0; c.pitch4 = 0; c.pad_ok = 0;
+  c.k_lethal = lethal_entry(p);
   c.cm_curv = kCmCurvature;
-  c.skip_polish = kSkipPolish * p.opt_tolerance;
+  c.sur_tol = kGuidedTolScale;
   c.guided = (p.costmap_guidance == NEOMPC_GUIDANCE_ON && p.costmap_mode == NEOMPC_COSTMAP_NEAREST) ? 1 : 0;
   c.state = nullptr;
   c.state_stride = state_stride_for(N);

@@ -107,7 +107,8 @@ int upload_tables(neompc_handle* h) {
 void rebuild_const(neompc_handle* h) {
   const SolverConst old = h->c;
   build_const(h->params, h->c);
-  h->c.cells = old.cells; h->c.cells4 = old.cells4; h->c.W = old.W; h->c.H = old.H;
+  h->c.cells = old.cells; h->c.cells4 = old.cells4; h->c.pad4 = old.pad4; h->c.pitch4 = old.pitch4; h->c.pad_ok = old.pad_ok;
+  h->c.W = old.W; h->c.H = old.H;
   h->c.inv_res = old.inv_res; h->c.inv_res_d = old.inv_res_d;
   h->c.origin_x = old.origin_x; h->c.origin_y = old.origin_y;
   h->c.fp_n = old.fp_n;
@@ -206,13 +207,13 @@ __global__ void pack_kernel(const neompc_optimizer_request* __restrict__ msgs, u
   reqs[i] = r;
 }
 
-// corner-packed copy of the costmap: one thread per entry of the padded (W+3) x (H+3) grid
-__global__ void corner_map_kernel(const uint8_t* __restrict__ cells, int W, int H, int lethal_byte,
+// corner-packed copy of the costmap: one thread per entry of the padded (W + 2 pad) x (H + 2 pad) grid
+__global__ void corner_map_kernel(const uint8_t* __restrict__ cells, int W, int H, int lethal_byte, int pad,
                                   uint32_t* __restrict__ out) {
-  const int pitch = corner_pitch(W);
-  const size_t total = corner_words(W, H);
+  const int pitch = corner_pitch(W, pad);
+  const size_t total = corner_words(W, H, pad);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int iy = (int)(i / pitch) - kCornerPad, ix = (int)(i % pitch) - kCornerPad;
+    const int iy = (int)(i / pitch) - pad, ix = (int)(i % pitch) - pad;
     out[i] = corner_word(cells, W, H, lethal_byte, ix, iy);
   }
 }
@@ -223,6 +224,31 @@ __global__ void reset_rows_kernel(float* state, int stride, const uint32_t* ids,
   const uint32_t id = ids[i];
   if (id >= rows) return;
   for (int k = threadIdx.x; k < stride; k += blockDim.x) state[(size_t)id * stride + k] = 0.0f;
+}
+
+// (Re)builds the corner-packed copy for the current costmap, encoding and reach (corner_pad_for: parameters and
+// resolution); enqueued on the handle's stream, no synchronise.
+int rebuild_corner_map(neompc_handle* h) {
+  if (h->c.cells == nullptr) { h->c.cells4 = nullptr; h->c.pad4 = 0; h->c.pitch4 = 0; h->c.pad_ok = 0; return NEOMPC_OK; }
+  int pad_ok = 0;
+  const int pad = corner_pad_for(h->params, h->resolution, &pad_ok);
+  const size_t words = corner_words(h->c.W, h->c.H, pad);
+  if (words > h->cells4_cap) {
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_cells4) cudaFree(h->d_cells4);
+    h->d_cells4 = nullptr; h->cells4_cap = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_cells4, words * sizeof(uint32_t)));
+    h->cells4_cap = words;
+  }
+  const unsigned blocks = (unsigned)((words + 255) / 256 < 4096 ? (words + 255) / 256 : 4096);
+  corner_map_kernel<<<blocks, 256, 0, h->stream>>>(h->d_cells, h->c.W, h->c.H, h->c.lethal_byte, pad, h->d_cells4);
+  NEOMPC_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  h->c.cells4 = h->d_cells4;
+  h->c.pad4 = pad;
+  h->c.pad_ok = pad_ok;
+  h->c.pitch4 = corner_pitch(h->c.W, pad);
+  return NEOMPC_OK;
 }
 
 int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
@@ -343,6 +369,10 @@ int neompc_set_params(neompc_handle* h, const neompc_params* params) {
     if (rc != NEOMPC_OK) return rc;
   }
   rebuild_const(h);
+  if (h->c.cells != nullptr && corner_pad_for(h->params, h->resolution) != h->c.pad4) {   // reach changed
+    int rc = rebuild_corner_map(h);
+    if (rc != NEOMPC_OK) return rc;
+  }
   return upload_tables(h);
 }
 
@@ -359,7 +389,7 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
   if (encoding != NEOMPC_ENC_OCCUPANCY && encoding != NEOMPC_ENC_NAV2_RAW)
     return fail(h, NEOMPC_ERR_INVALID, "unknown costmap encoding");
   if (cells == nullptr) {                      // free space
-    h->c.cells = nullptr; h->c.cells4 = nullptr; h->c.W = h->c.H = 0;
+    h->c.cells = nullptr; h->c.cells4 = nullptr; h->c.pad4 = h->c.pitch4 = h->c.pad_ok = 0; h->c.W = h->c.H = 0;
     return NEOMPC_OK;
   }
   if (width == 0 || height == 0 || width > 65535u || height > 65535u || !(resolution > 0.0))
@@ -372,18 +402,9 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
     NEOMPC_CUDA(h, cudaMalloc(&h->d_cells, bytes));
     h->cells_cap = bytes;
   }
-  const size_t words = corner_words((int)width, (int)height);
-  if (words > h->cells4_cap) {
-    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (h->d_cells4) cudaFree(h->d_cells4);
-    h->d_cells4 = nullptr; h->cells4_cap = 0;
-    NEOMPC_CUDA(h, cudaMalloc(&h->d_cells4, words * sizeof(uint32_t)));
-    h->cells4_cap = words;
-  }
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_cells, cells, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                  h->stream));
   h->c.cells = h->d_cells;
-  h->c.cells4 = h->d_cells4;
   h->c.W = (int)width; h->c.H = (int)height;
   h->c.inv_res_d = 1.0 / resolution;
   h->c.inv_res = (float)(1.0 / resolution);
@@ -395,12 +416,8 @@ static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_de
     h->c.lethal_byte = encoding == NEOMPC_ENC_NAV2_RAW ? 254 : 100;
     h->c.cm_scale = 1.0f / (float)h->c.lethal_byte;
   }
-  {
-    const unsigned blocks = (unsigned)((words + 255) / 256 < 4096 ? (words + 255) / 256 : 4096);
-    corner_map_kernel<<<blocks, 256, 0, h->stream>>>(h->d_cells, h->c.W, h->c.H, h->c.lethal_byte, h->d_cells4);
-    NEOMPC_CUDA(h, cudaGetLastError());
-    h->launches += 1;
-  }
+  int rc = rebuild_corner_map(h);
+  if (rc != NEOMPC_OK) return rc;
   if (enc_changed) return upload_tables(h);
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   return NEOMPC_OK;

@@ -33,7 +33,9 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.c.cm_scale = 1.0f / (float)e.c.lethal_byte;
   e.c.W = W; e.c.H = H;
   if (cells != nullptr) {
-    build_corner_map(cells, W, H, e.c.lethal_byte, e.cells4);
+    e.c.pad4 = corner_pad_for(*p, res, &e.c.pad_ok);
+    e.c.pitch4 = corner_pitch(W, e.c.pad4);
+    build_corner_map(cells, W, H, e.c.lethal_byte, e.c.pad4, e.cells4);
     e.c.cells4 = e.cells4.data();
   }
   e.c.inv_res = (float)(1.0 / res);
@@ -45,9 +47,12 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   e.c.state_rows = state_rows;
   if (getenv("HOSTSIM_PINALPHA")) e.c.pin_alpha = atof(getenv("HOSTSIM_PINALPHA"));
   if (getenv("HOSTSIM_CMCURV")) e.c.cm_curv = atof(getenv("HOSTSIM_CMCURV"));
-  if (getenv("HOSTSIM_SKIPPOLISH")) e.c.skip_polish = atof(getenv("HOSTSIM_SKIPPOLISH")) * p->opt_tolerance;
+  if (getenv("HOSTSIM_SURTOL")) e.c.sur_tol = atof(getenv("HOSTSIM_SURTOL"));
   if (getenv("HOSTSIM_PAIREPS")) e.c.pair_eps = atof(getenv("HOSTSIM_PAIREPS"));
   if (getenv("HOSTSIM_TOLX")) { e.c.tol_x = atof(getenv("HOSTSIM_TOLX")); e.c.pin_alpha = 0.0f; }
+  if (getenv("HOSTSIM_TOLSCALE")) { const float k = atof(getenv("HOSTSIM_TOLSCALE")); e.c.tol_pg *= k; e.c.tol_f *= k; e.c.tol_x *= k; }
+  if (getenv("HOSTSIM_TOLF")) e.c.tol_f *= atof(getenv("HOSTSIM_TOLF"));
+  if (getenv("HOSTSIM_TOLPG")) e.c.tol_pg *= atof(getenv("HOSTSIM_TOLPG"));
   if (tol_pg > 0) e.c.tol_pg = tol_pg;
   if (tol_f >= 0) e.c.tol_f = tol_f;
 }
