@@ -42,9 +42,10 @@ _W = {}
 PER_GPU_BATCH = {"c2": 4096, "c3": 65536, "c4": 131072, "c5": 100000}
 
 
-def _cpu_init(cfg, batch, seed_off):
+def _cpu_init(cfg, batch, use_port):
     os.environ["OMP_NUM_THREADS"] = "1"
     import oracle
+    from oracle import ref_runner
     from oracle.costmap import GridCostmap, FreeSpaceCostmap
     from neo_mpc_planner2_b200 import workloads
     wl = workloads.config(cfg, batch=batch)
@@ -53,44 +54,52 @@ def _cpu_init(cfg, batch, seed_off):
     _W["cm"] = (GridCostmap(wl.cells, wl.resolution, wl.origin_x, wl.origin_y) if wl.cells is not None
                 else FreeSpaceCostmap())
     _W["oracle"] = oracle
+    # the UNMODIFIED reference (oracle/_ref, byte-compiled from /root/reference by oracle/build_ref.py) under ROS stand-ins
+    _W["ref"] = None if use_port or not ref_runner.available() else ref_runner.ReferenceSolver(wl.params, _W["cm"], wl.footprint)
 
 
 def _cpu_solve(i):
-    """One reference solve, exactly the reference's call (srv.py:363-364): cold start, SLSQP, ftol = opt_tolerance."""
+    """One reference solve, exactly the reference's call (srv.py:363-364): cold start, SLSQP, ftol = opt_tolerance —
+    on the reference's own objects when oracle/_ref is there, else on the oracle port of the same lines."""
     oracle, wl, p, cm = _W["oracle"], _W["wl"], _W["p"], _W["cm"]
     from oracle.mpc_oracle import footprint_world
     prob = oracle.Problem.from_record(wl.requests[i])
-    fpw = footprint_world(wl.footprint, prob.pose_x, prob.pose_y, prob.pose_yaw)
-    res = oracle.slsqp_solve(p, cm, fpw, prob)
+    if _W["ref"] is not None:
+        res = _W["ref"].solve(prob)
+    else:
+        fpw = footprint_world(wl.footprint, prob.pose_x, prob.pose_y, prob.pose_yaw)
+        res = oracle.slsqp_solve(p, cm, fpw, prob)
     return i, float(res.fun), res.x.astype(np.float64)
 
 
-def _cpu_solve_tight(i):
-    """The same problem converged tightly (ftol 1e-10, best of a cold start and a start from the ftol = opt_tolerance
-    point): the yardstick for 'how far is a first control from the optimum' (untimed; only with --dump-ref)."""
+def _cpu_solve_tight(args):
+    """The same problem converged tightly with the reference's solver (ftol 1e-10): best of a cold start, a start from the
+    ftol = opt_tolerance point and a start from the GPU's solution — the yardstick for 'how far is a first control from
+    the best known optimum' (untimed; only with --dump-ref)."""
+    i, x_gpu = args
     oracle, wl, p, cm = _W["oracle"], _W["wl"], _W["p"], _W["cm"]
     from oracle.mpc_oracle import footprint_world
     prob = oracle.Problem.from_record(wl.requests[i])
     fpw = footprint_world(wl.footprint, prob.pose_x, prob.pose_y, prob.pose_yaw)
     res = oracle.slsqp_solve(p, cm, fpw, prob)
-    a = oracle.slsqp_solve(p, cm, fpw, prob, x0=res.x, ftol=1e-10, maxiter=400)
-    b = oracle.slsqp_solve(p, cm, fpw, prob, ftol=1e-10, maxiter=400)
-    best = a if a.fun <= b.fun else b
+    cands = [oracle.slsqp_solve(p, cm, fpw, prob, x0=res.x, ftol=1e-10, maxiter=400),
+             oracle.slsqp_solve(p, cm, fpw, prob, ftol=1e-10, maxiter=400)]
+    if x_gpu is not None:
+        cands.append(oracle.slsqp_solve(p, cm, fpw, prob, x0=np.asarray(x_gpu, dtype=np.float64), ftol=1e-10, maxiter=400))
+    best = min(cands, key=lambda r: r.fun)
     return i, float(best.fun), best.x.astype(np.float64)
 
 
-def cpu_reference_rate(cfg, sample, cores, repeats=1):
-    """solves/s of the reference algorithm on `sample` problems of the workload with `cores` processes."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg, PER_GPU_BATCH[cfg], 0)) as pool:
-        pool.map(_cpu_solve, range(min(cores, sample)))          # warm the workers (imports, first call)
-        times, last = [], None
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            last = pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
-            times.append(time.perf_counter() - t0)
-    return sample / min(times), times, last
+def common_config(args, n_steps, opt_tolerance, batch_per_gpu):
+    """The `config` object — the same keys and values in both arms (`--impl ours` and `--impl reference`)."""
+    wl_name, _ = _workload_name(args.config)
+    return {"workload": wl_name, "batch_per_gpu": int(batch_per_gpu), "control_steps": int(n_steps),
+            "opt_tolerance": float(opt_tolerance), "cold_start": True,
+            "footprint_mode": "moving (opt-in, not the reference's objective)" if args.footprint_mode else "static (reference)",
+            "costmap_mode": "bilinear (opt-in, not the reference's objective)" if args.costmap_mode else "nearest cell (reference)",
+            "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
+            "parallelism": (f"batch sharded over {args.gpus} GPU(s), one NCCL all-gather of (vx,vy,omega) per step"
+                            if args.gpus > 1 else "single GPU")}
 
 
 def run_reference(args):
@@ -101,10 +110,13 @@ def run_reference(args):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    sample = args.cpu_sample or {"c2": 1024, "c3": 128, "c4": 32, "c5": 128}[args.config]
+    from oracle import ref_runner
+    use_port = bool(args.port) or not ref_runner.available()
+    sample = args.cpu_sample or {"c2": 512, "c3": 64, "c4": 16, "c5": 64}[args.config]
+    per_gpu = args.batch or PER_GPU_BATCH[args.config]
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.config, args.batch or PER_GPU_BATCH[args.config], 0)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(args.config, per_gpu, use_port)) as pool:
         for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_solve, range(min(cores, sample)))
         t0 = time.perf_counter()
@@ -112,19 +124,27 @@ def run_reference(args):
         for _ in range(args.steps):
             last = pool.map(_cpu_solve, range(sample), chunksize=max(1, sample // (cores * 4)))
         dt = time.perf_counter() - t0
-        tight = pool.map(_cpu_solve_tight, range(min(sample, 4 * cores))) if args.dump_ref else None   # untimed
+        tight = None
+        if args.dump_ref:                                           # untimed: tightly converged yardstick
+            kt = min(sample, 4 * cores)
+            xg = np.load(args.gpu_plan)["plan"] if args.gpu_plan else None
+            tight = pool.map(_cpu_solve_tight, [(i, None if xg is None else xg[i]) for i in range(kt)])
     if args.dump_ref and last:
         np.savez(args.dump_ref, J=np.array([r[1] for r in last]), x=np.stack([r[2] for r in last]),
                  J_tight=np.array([r[1] for r in tight]), x_tight=np.stack([r[2] for r in tight]))
     value = args.steps * sample / dt
-    wl_name, n_steps = _workload_name(args.config)
+    from neo_mpc_planner2_b200 import workloads
+    wl = workloads.config(args.config, batch=64)
+    kind = "port" if use_port else "reference"
+    how = ("oracle port of srv.py:204-269 + :363-364 (oracle/mpc_oracle.py)" if use_port else
+           "the UNMODIFIED mpc_optimization_server.py (oracle/_ref, byte-compiled from /root/reference) under ROS stand-in "
+           "modules: its own objective / f_constraint / bnds / cons through minimize(SLSQP) exactly as srv.py:363-364")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "control_steps": n_steps, "opt_tolerance": 1e-3,
-                   "solver": "scipy SLSQP, finite-difference gradients (oracle port of srv.py:363-364)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "per_core": value / cores,
+        "config": common_config(args, wl.control_steps, wl.params["opt_tolerance"], per_gpu),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "per_core": value / cores, "how": how,
                          "sample": f"first {sample} problems of the workload per step, cold start, "
                                    f"multiprocessing.Pool({cores})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -152,6 +172,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.power_w = []
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
@@ -172,6 +193,7 @@ class ClockSampler(threading.Thread):
         while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.power_w.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if r & bit:
@@ -185,7 +207,8 @@ class ClockSampler(threading.Thread):
         if self.is_alive():
             self.join(timeout=1.0)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": float(max(self.power_w)) if self.power_w else None}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -310,6 +333,26 @@ def run_ours(args):
     e2e_value = world * n * e2e_steps / float(t.item())
     clocks = sampler.stop()
 
+    # ---- sustained: >= 2 s of back-to-back solve kernels (no L2 flush, no host gaps) — does the flushed 20-step figure
+    # survive once the board is at temperature and power?  Reported next to `value`, which stays the flushed figure.
+    k_est = max(float(np.mean(kern_ms)), 1e-3)
+    n_sus = int(args.sustained_s * 1e3 / k_est) + 1
+    sus_sampler = ClockSampler(local)
+    sus_sampler.start()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record(stream)
+    for k in range(n_sus):
+        solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_twist[k & 1].data_ptr(), None, stream.cuda_stream)
+    s1.record(stream)
+    barrier()
+    sus_ms = s0.elapsed_time(s1)
+    sus_clocks = sus_sampler.stop()
+    sustained = {"seconds": sus_ms / 1e3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
+                 "value_per_gpu": n * n_sus / (sus_ms * 1e-3), "unit": UNIT, "l2": "not flushed (back-to-back launches)",
+                 "sm_mhz_median": sus_clocks["sm_mhz"], "power_w_max": sus_clocks["power_w_max"],
+                 "reasons": sus_clocks["reasons"], "clock_samples": sus_clocks["samples"]}
+
     # ---- latency of ONE request through the message-level entry (what the controller plugin calls every tick,
     # replacing the ROS service hop + scipy solve): neompc_solve_msgs, stateful instance 0, host buffers
     lat = None
@@ -365,15 +408,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, "batch_per_gpu": n, "control_steps": n_steps,
-                       "opt_tolerance": float(wl.params["opt_tolerance"]), "lanes_per_instance": G,
-                       "steps_per_lane": S, "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
-                       "parallelism": f"batch sharded over {world} GPU(s), one NCCL all-gather of (vx,vy,omega) per step, "
-                                      "overlapped with the next step's solve on a second stream"
-                       if world > 1 else "single GPU", "cold_start": True,
-                       "footprint_mode": "moving (opt-in, not the reference's objective)" if args.footprint_mode else "static (reference)",
-                       "costmap_mode": "bilinear (opt-in, not the reference's objective)" if args.costmap_mode else "nearest cell (reference)",
-                       "iters_median": iters_med, "evals_mean": evals_mean},
+            "config": common_config(args, n_steps, wl.params["opt_tolerance"], n),
+            "arm": {"lanes_per_instance": G, "steps_per_lane": S, "iters_median": iters_med, "evals_mean": evals_mean,
+                    "costmap_guidance": "off (round-1 strategy)" if args.costmap_guidance else "on",
+                    "gather": "overlapped with the next step's solve on a second stream" if world > 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
                          "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
@@ -385,22 +423,31 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "single_request_latency": lat,
+            "sustained": sustained,
         }
         if world == 1 and not args.no_cpu_baseline and not args.footprint_mode and not args.costmap_mode:
             # the reference arm in a FRESH interpreter (no CUDA context / torch thread pools in the forked workers)
             import subprocess
-            sample = args.cpu_sample or {"c2": 2048, "c3": 256, "c4": 64, "c5": 256}[args.config]   # ~15 core-seconds
-            env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
             import tempfile
-            dump = os.path.join(tempfile.mkdtemp(prefix="neompc_ref_"), "ref.npz")
-            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config",
-                                  args.config, "--steps", "2", "--warmup", "1", "--cpu-sample", str(sample),
-                                  "--batch", str(per_gpu), "--dump-ref", dump],
-                                 capture_output=True, text=True, env=env, timeout=600)
+            sample = args.cpu_sample or {"c2": 1024, "c3": 128, "c4": 32, "c5": 128}[args.config]   # ~10-30 s of CPU work
+            env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+            tmpd = tempfile.mkdtemp(prefix="neompc_ref_")
+            dump, gplan = os.path.join(tmpd, "ref.npz"), os.path.join(tmpd, "gpu_plan.npz")
+            sub = wl.requests[:sample]
+            _, plan = solver.solve(sub, want_plan=True)
+            np.savez(gplan, plan=plan)
+            base = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                    "--batch", str(per_gpu)]
+            res = subprocess.run(base + ["--steps", "1", "--warmup", "1", "--cpu-sample", str(sample), "--dump-ref", dump,
+                                         "--gpu-plan", gplan], capture_output=True, text=True, env=env, timeout=900)
             try:
                 ref = json.loads(res.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = ref["cpu_baseline"]
-                line["cpu_baseline"]["sample"] += f", 2 timed passes, {ref['ms_per_step'] / 1e3:.1f} s each"
+                line["cpu_baseline"]["sample"] += f", 1 timed pass of {ref['ms_per_step'] / 1e3:.1f} s"
+                if ref["cpu_baseline"]["kind"] == "reference":       # the oracle port of the same lines, for comparison
+                    rp = subprocess.run(base + ["--port", "--steps", "1", "--warmup", "1", "--cpu-sample", str(sample)],
+                                        capture_output=True, text=True, env=env, timeout=900)
+                    line["cpu_baseline"]["oracle_port_value"] = json.loads(rp.stdout.strip().splitlines()[-1])["value"]
                 # cost residual J_gpu - J_scipy on the same problems (BASELINE.json metric), both evaluated by the
                 # float64 oracle objective at the respective solutions (untimed; checker use of oracle/)
                 import oracle
@@ -408,33 +455,39 @@ def run_ours(args):
                 from oracle.mpc_oracle import footprint_world
                 refd = np.load(dump)
                 k = len(refd["J"])
-                sub = wl.requests[:k]
-                _, plan = solver.solve(sub, want_plan=True)
                 pm = oracle.MpcParams(**wl.params)
                 cm = GridCostmap(wl.cells, wl.resolution, wl.origin_x, wl.origin_y) if wl.cells is not None else None
                 fpl = np.array([cm.getFootprintCost(footprint_world(wl.footprint, float(r["pose_x"]), float(r["pose_y"]),
                                 float(r["pose_yaw"]))) == 1.0 for r in sub]) if cm is not None else None
                 Jg = oracle.objective_batch(pm, cm, sub, plan.astype(np.float64), fp_lethal=fpl)
                 dJ = Jg - refd["J"]
+                tol = float(wl.params["opt_tolerance"])
                 du = np.abs(plan[:, :3].astype(np.float64) - refd["x"][:, :3]).max(axis=1)
                 line["cost_residual"] = {
                     "definition": "J_gpu - J_scipy(ftol=opt_tolerance), float64 oracle objective, same problems",
                     "problems": int(k), "median": float(np.median(dJ)), "p99": float(np.percentile(dJ, 99)),
                     "max": float(dJ.max()), "frac_worse_than_1e-4": float((dJ > 1e-4).mean()),
+                    "frac_worse_than_opt_tol": float((dJ > tol).mean()),
                     "first_control_abs_diff_median": float(np.median(du)),
                     "first_control_abs_diff_p90": float(np.percentile(du, 90))}
                 if "x_tight" in refd:
-                    # the same comparison against the tightly converged reference optimum (ftol 1e-10): separates the
-                    # solver's own error from scipy's early stop at ftol = opt_tolerance
+                    # the same comparison against the best tightly converged reference optimum known (ftol 1e-10; cold
+                    # start, from the ftol = opt_tolerance point, from the GPU's point): separates the solver's own error
+                    # from scipy's early stop.  Problems where the GPU's plan is cheaper than that optimum by more than
+                    # 1e-5 say nothing about velocities (the reference sits in a worse basin): counted, not compared.
                     kt = len(refd["J_tight"])
-                    dut = np.abs(plan[:kt, :3].astype(np.float64) - refd["x_tight"][:, :3]).max(axis=1)
+                    gap = Jg[:kt] - refd["J_tight"]
+                    keep = gap >= -1e-5
+                    dut = np.abs(plan[:kt, :3].astype(np.float64) - refd["x_tight"][:, :3]).max(axis=1)[keep]
                     dus = np.abs(refd["x"][:kt, :3] - refd["x_tight"][:, :3]).max(axis=1)
                     line["cost_residual"].update({
-                        "tight_problems": int(kt),
-                        "J_gpu_minus_J_scipy_tight_median": float(np.median(Jg[:kt] - refd["J_tight"])),
-                        "J_gpu_minus_J_scipy_tight_max": float((Jg[:kt] - refd["J_tight"]).max()),
+                        "tight_problems": int(kt), "gpu_plan_cheaper_than_tight_scipy": int((~keep).sum()),
+                        "J_gpu_minus_J_scipy_tight_median": float(np.median(gap)),
+                        "J_gpu_minus_J_scipy_tight_p99": float(np.percentile(gap, 99)),
+                        "J_gpu_minus_J_scipy_tight_max": float(gap.max()),
                         "first_control_vs_tight_scipy_median": float(np.median(dut)),
                         "first_control_vs_tight_scipy_p90": float(np.percentile(dut, 90)),
+                        "first_control_vs_tight_scipy_p99": float(np.percentile(dut, 99)),
                         "scipy_at_opt_tolerance_vs_tight_scipy_median": float(np.median(dus)),
                         "scipy_at_opt_tolerance_vs_tight_scipy_p90": float(np.percentile(dus, 90))})
             except Exception as exc:  # keep the GPU numbers even if the CPU arm failed
@@ -465,9 +518,12 @@ def main():
     ap.add_argument("--costmap-guidance", type=int, default=0, choices=[0, 1],
                     help="0 = costmap guidance on (default); 1 = off: solve on the reference's objective from the start "
                          "(the round-1 strategy; A/B measurements)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the back-to-back run of the `sustained` record")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ref", default="", help="reference arm: save per-problem J and x of the last pass (npz)")
+    ap.add_argument("--gpu-plan", default="", help="reference arm: npz with the GPU's plans, a third start of the tight solves")
+    ap.add_argument("--port", action="store_true", help="reference arm: time the oracle port instead of oracle/_ref")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,7 @@ stack keeps working without touching the plugin: only the Python executable is s
   * dynamic parameters                                                               srv.py:405-439
 
 ``rclpy``, ``neo_srvs2`` and the message packages are imported when this module is imported; they are not part of this
-repository's image, so the module is exercised in the tests under the stand-in modules of ``tests/golden/ros_stubs.py``
+repository's image, so the module is exercised in the tests under the stand-in modules of ``oracle/ros_stubs.py``
 (the same ones that drive the unmodified reference for the golden vectors).  There is no CPU path: constructing the node
 without a CUDA device raises.
 

@@ -9,7 +9,9 @@ returns early at srv.py:279-282).
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
+import os
 import sys
 import types
 from dataclasses import dataclass, field
@@ -250,6 +252,20 @@ def load_reference(path="/root/reference/neo_mpc_planner2/mpc_optimization_serve
     spec = importlib.util.spec_from_file_location("ref_mpc_optimization_server", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    return mod
+
+
+REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "mpc_optimization_server.pyc")
+
+
+def load_reference_compiled(path=REF_PYC):
+    """Load the byte-compiled, unmodified reference module (oracle/_ref, built by oracle/build_ref.py from the sources
+    where they lie under /root/reference): this is what travels to the GPU box, where /root/reference does not exist."""
+    install()
+    loader = importlib.machinery.SourcelessFileLoader("ref_mpc_optimization_server", path)
+    spec = importlib.util.spec_from_loader("ref_mpc_optimization_server", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
     return mod
 
 

@@ -3,7 +3,7 @@
 
 Runs only in the build container (needs /root/reference).  It imports
 ``/root/reference/neo_mpc_planner2/mpc_optimization_server.py`` under the ROS stub modules of
-``ros_stubs.py``, plugs the declared costmap fake (``oracle/costmap.py``) into it, drives the
+``oracle/ros_stubs.py``, plugs the declared costmap fake (``oracle/costmap.py``) into it, drives the
 reference's own ``objective`` / ``f_constraint`` / ``minimize`` call / ``optimizer`` handler and
 writes inputs + outputs to JSON.  While generating, it asserts that the oracle restatement
 (``oracle/mpc_oracle.py``) reproduces every number BIT-EXACTLY; ``tests/test_oracle_golden.py``
@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import ros_stubs  # noqa: E402
+from oracle import ros_stubs  # noqa: E402
 import oracle  # noqa: E402
 from oracle.costmap import GridCostmap, FreeSpaceCostmap  # noqa: E402
 from oracle.mpc_oracle import footprint_world  # noqa: E402

@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import ros_stubs  # noqa: E402
+from oracle import ros_stubs  # noqa: E402
 import oracle  # noqa: E402
 from oracle.costmap import GridCostmap  # noqa: E402
 from make_golden import set_request_state, set_footprint, make_request_msg, FakeClock  # noqa: E402

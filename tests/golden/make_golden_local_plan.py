@@ -2,7 +2,7 @@
 """Golden vectors for the predicted-path output from the UNMODIFIED reference.
 
 Runs only in the build container (needs /root/reference).  Loads
-``/root/reference/neo_mpc_planner2/mpc_optimization_server.py`` under the ROS stubs of ``ros_stubs.py``, replaces the
+``/root/reference/neo_mpc_planner2/mpc_optimization_server.py`` under the ROS stubs of ``oracle/ros_stubs.py``, replaces the
 server's TF buffer by one that answers (the stub's default raises, which makes ``publishLocalPlan`` return early) and
 its publisher by one that records, calls the reference's own ``publishLocalPlan(x)`` (srv.py:271-310) and writes
 inputs + the published poses to ``local_plan_golden.json``.  Asserts ``==`` against ``oracle.local_plan`` while doing so.
@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import ros_stubs  # noqa: E402
+from oracle import ros_stubs  # noqa: E402
 import oracle  # noqa: E402
 
 README = oracle.MpcParams.readme_sample().as_dict()

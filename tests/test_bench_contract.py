@@ -18,8 +18,21 @@ def test_reference_arm_json_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "mpc_solves_per_sec" and line["unit"] == "solves/s"
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_runner
+    want = "reference" if ref_runner.available() else "port"       # oracle/_ref: the unmodified reference, byte-compiled
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == want and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+    # `config` carries the same keys in both arms (the driver compares them)
+    assert set(line["config"]) == {"workload", "batch_per_gpu", "control_steps", "opt_tolerance", "cold_start",
+                                   "footprint_mode", "costmap_mode", "l2", "parallelism"}
+
+
+def test_reference_arm_port_flag():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--port", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample", "8", "--config", "c2"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stderr[-500:]
+    assert json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -12,7 +12,7 @@ from neo_mpc_planner2_b200 import workloads
 from neo_mpc_planner2_b200.abi import REQUEST_DTYPE, README_SAMPLE
 from tests.hostsim import HostSim
 from tests.util import (setup_workload, footprint_lethal_flags, near_cell_edge, feasibility_violation,
-                        scipy_solutions)
+                        scipy_solutions, scipy_reference)
 
 
 def _hs(wl, **knobs):
@@ -60,20 +60,41 @@ def test_projection_properties():
             assert d_proj <= d_best + 1e-5
 
 
-@pytest.mark.parametrize("cfg,n_steps,count", [("c1", 3, 1), ("c2", 3, 48), ("c3", 10, 12)])
+@pytest.mark.parametrize("cfg,n_steps,count", [("c1", 3, 1), ("c2", 3, 256), ("c3", 10, 32)])
 def test_solver_reaches_scipy_cost(cfg, n_steps, count):
-    wl, p, cm = setup_workload(cfg, 64 if cfg != "c1" else None, n_steps)
+    """J_hostsim - J_scipy(ftol = opt_tolerance) on the reference's objective: p99 <= opt_tolerance, max <= 2 opt_tolerance,
+    median <= 0, at most 1 in 16 worse by more than 1e-4 (the same gates as the GPU tests)."""
+    batch = max(count, 64) if cfg != "c1" else None
+    wl, p, cm = setup_workload(cfg, batch, n_steps)
     out, plan = _hs(wl).solve(wl.requests)
     assert feasibility_violation(wl.params, plan) <= 1e-6
     fpl = footprint_lethal_flags(wl, cm)
     Jg = oracle.objective_batch(p, cm, wl.requests, plan.astype(np.float64), fp_lethal=fpl)
     idx = list(range(min(count, wl.batch)))
-    ref = scipy_solutions(wl, p, cm, idx)
-    dJ = np.array([Jg[i] - float(r.fun) for i, (r, _) in zip(idx, ref)])
-    assert dJ.max() <= 5 * p.opt_tolerance
+    ref = scipy_reference(cfg, batch, n_steps, idx)
+    dJ = np.array([Jg[i] - r["fun"] for i, r in zip(idx, ref)])
+    assert dJ.max() <= 2 * p.opt_tolerance, dJ.max()
+    assert np.percentile(dJ, 99) <= p.opt_tolerance or count < 100
     assert (dJ > 1e-4).sum() <= max(1, len(dJ) // 16)
     assert np.median(dJ) <= 0.0
     assert (out["status"] != 1).all()
+
+
+def test_costmap_guidance_improves_on_the_unguided_solve():
+    """Costmap guidance (solve first on the interpolated costmap term, then on the reference's objective) against the
+    round-1 strategy (reference's objective from the start) on 512 C2 problems: the tail of J - J_scipy shrinks."""
+    wl, p, cm = setup_workload("c2", 512, 3)
+    fpl = footprint_lethal_flags(wl, cm)
+    ref = scipy_reference("c2", 512, 3, range(512))
+    Js = np.array([r["fun"] for r in ref])
+    worst = {}
+    for name, knob in (("guided", 0), ("unguided", 1)):
+        out, plan = _hs(wl, costmap_guidance=knob).solve(wl.requests)
+        dJ = oracle.objective_batch(p, cm, wl.requests, plan.astype(np.float64), fp_lethal=fpl) - Js
+        worst[name] = (np.percentile(dJ, 99), (dJ > 1e-4).mean(), np.median(dJ))
+    assert worst["guided"][0] <= 0.0 < worst["unguided"][0], worst          # p99: better than scipy vs worse than scipy
+    assert worst["guided"][1] <= 0.5 * worst["unguided"][1] + 1e-9, worst
+    assert worst["guided"][2] <= worst["unguided"][2], worst
 
 
 def test_kat_solution_close_to_tight_scipy(golden):
@@ -193,18 +214,25 @@ def test_degenerate_weights(over):
 def test_code_default_parameters_against_scipy():
     """The reference's CODE defaults (srv.py:49-75: all weights 0.5, limits 0.5, opt_tolerance 1e-5, horizon 0.5 s) are a
     harder regime than the README sample: the control-term kink weighs 10x more and so does the costmap staircase, and
-    scipy converges tightly.  Against it the solver is on par in the median and loses / wins the staircase basins about
-    equally often (measured on 512 problems: 27 % worse by > 1e-4, 27 % better, 47 % within 1e-4)."""
+    scipy converges tightly.  Round 1: 27 % of the problems worse than scipy by > 1e-4, p99 +4.8e-2; with costmap guidance,
+    the 1e-4 smoothing floor and no pinned-arc stop at this tolerance: 3 %, p99 +3.5e-3 (512 problems)."""
     code = oracle.MpcParams().as_dict()
     code.pop("control_steps")
-    wl, p, cm = setup_workload("c2", 96, 3, **code)
+    wl, p, cm = setup_workload("c2", 512, 3, **code)
     out, plan = _hs(wl).solve(wl.requests)
     assert feasibility_violation(wl.params, plan) <= 1e-6
     fpl = footprint_lethal_flags(wl, cm)
     Jg = oracle.objective_batch(p, cm, wl.requests, plan.astype(np.float64), fp_lethal=fpl)
-    ref = scipy_solutions(wl, p, cm, range(96))
-    dJ = np.array([Jg[i] - float(r.fun) for i, (r, _) in enumerate(ref)])
-    assert np.median(dJ) <= 2e-5
-    assert (dJ > 1e-4).mean() <= 0.4 and (dJ > 1e-2).mean() <= 0.1
-    assert (dJ < -1e-4).mean() >= 0.1                  # it wins basins too
+    ref = scipy_reference("c2", 512, 3, range(512), param_over=code)
+    dJ = np.array([Jg[i] - r["fun"] for i, r in enumerate(ref)])
+    assert np.median(dJ) <= 0.0
+    assert (dJ > 1e-4).mean() <= 0.05 and np.percentile(dJ, 99) <= 5e-3, ((dJ > 1e-4).mean(), np.percentile(dJ, 99))
+    assert (dJ < -1e-4).mean() >= 0.3                  # it wins basins far more often than it loses them
     assert (out["status"] != 1).all()
+    # free space (no staircase): never worse than scipy by more than the smoothing bias
+    wl2, p2, _ = setup_workload("c2", 256, 3, **code)
+    wl2.cells = None
+    out2, plan2 = _hs(wl2).solve(wl2.requests)
+    ref2 = scipy_reference("c2", 256, 3, range(256), param_over=code, nomap=True)
+    dJ2 = oracle.objective_batch(p2, None, wl2.requests, plan2.astype(np.float64)) - np.array([r["fun"] for r in ref2])
+    assert dJ2.max() <= 2e-5, dJ2.max()

@@ -1,5 +1,5 @@
 """The ROS 2 node shim for un-modified clients, exercised under the stand-in ROS modules of
-tests/golden/ros_stubs.py (this image has no rclpy): same node name, service, topics and parameter names as the
+oracle/ros_stubs.py (this image has no rclpy): same node name, service, topics and parameter names as the
 reference; answers equal the library's direct answers; the published Path equals the oracle's publishLocalPlan."""
 import os
 import sys
@@ -16,8 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture()
 def ros(monkeypatch):
-    sys.path.insert(0, os.path.join(HERE, "golden"))
-    import ros_stubs
+    from oracle import ros_stubs
     saved = {k: v for k, v in sys.modules.items()}
     ros_stubs.install()
     sys.modules.pop("neo_mpc_planner2_b200.ros_node", None)
@@ -25,7 +24,6 @@ def ros(monkeypatch):
     for k in list(sys.modules):
         if k not in saved:
             del sys.modules[k]
-    sys.path.remove(os.path.join(HERE, "golden"))
 
 
 class Recorder:
