@@ -28,6 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv:      # the CPU arm: one thread per worker process (set before numpy loads its BLAS)
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ.setdefault(_v, "1")
+
 import numpy as np  # noqa: E402
 
 METRIC = "mpc_solves_per_sec"

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Recipe for ``oracle/_ref``: byte-compiles the UNMODIFIED reference server module from the sources where they lie
-(``/root/reference/neo_mpc_planner2/mpc_optimization_server.py``) into ``oracle/_ref/mpc_optimization_server.pyc``.
+(``/root/reference/neo_mpc_planner2/mpc_optimization_server.py``) into ``oracle/_ref/mpc_optimization_server.pyc.bin``.
 
 The reference's hot path is Python, so "compiling the reference" is ``py_compile``; the .pyc is a build output (listed in
 .gitignore, shipped to the GPU box like the built .so files) — no reference source is copied into the repository.
@@ -19,7 +19,7 @@ import sys
 
 SRC = "/root/reference/neo_mpc_planner2/mpc_optimization_server.py"
 OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
-OUT = os.path.join(OUT_DIR, "mpc_optimization_server.pyc")
+OUT = os.path.join(OUT_DIR, "mpc_optimization_server.pyc.bin")
 
 
 def build(src: str = SRC) -> str | None:

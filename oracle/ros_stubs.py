@@ -255,7 +255,7 @@ def load_reference(path="/root/reference/neo_mpc_planner2/mpc_optimization_serve
     return mod
 
 
-REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "mpc_optimization_server.pyc")
+REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "mpc_optimization_server.pyc.bin")
 
 
 def load_reference_compiled(path=REF_PYC):
