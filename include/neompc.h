@@ -94,10 +94,12 @@ typedef struct neompc_params {
   float prediction_horizon;                                        /* srv.py:73 */
   int32_t control_steps;                                           /* srv.py:75; 1..NEOMPC_MAX_CONTROL_STEPS */
   int32_t max_iterations;      /* L-BFGS iteration cap (default 100 = SLSQP's maxiter default) */
-  int32_t lbfgs_memory;        /* history pairs, 1..8 (default 3) */
+  int32_t lbfgs_memory;        /* history pairs, 1..8 (default 1: with the block-diagonal preconditioner one pair does as well as 3 or 6;
+                                  other values take the general kernel build) */
   float control_smoothing;     /* epsilon of sqrt(r^2+eps^2) used for the control-term kink (srv.py:253-254);
-                                  default: 10 * opt_tolerance clamped to [1e-3, 1e-2] */
-  int32_t lanes_per_instance;  /* 1,2,4,8,16,32 lanes of a warp cooperate on one instance; 0 = auto by control_steps */
+                                  default: 10 * opt_tolerance clamped to [1e-4, 1e-2] */
+  int32_t lanes_per_instance;  /* 1,2,3,4,5,6,8,10,16 or 32 lanes of a warp cooperate on one instance (a size that would need more than
+                                  4 steps per lane is raised to the next that fits); 0 = auto by control_steps */
   int32_t footprint_mode;      /* NEOMPC_FOOTPRINT_* ; 0 = the reference's behaviour */
   int32_t costmap_mode;        /* NEOMPC_COSTMAP_* ; 0 = the reference's behaviour */
   int32_t costmap_guidance;    /* NEOMPC_GUIDANCE_* ; 0 = on.  Solver strategy only: the objective, and with it every reported
@@ -136,7 +138,8 @@ enum {
   NEOMPC_FLAG_COLLISION = 1,            /* self.collision after this call        (srv.py:338-339,380-382) */
   NEOMPC_FLAG_COLLISION_FOOTPRINT = 2,  /* self.collision_footprint              (srv.py:343-347) */
   NEOMPC_FLAG_NEW_GOAL = 4,             /* the new-goal reset ran                (srv.py:358-361) */
-  NEOMPC_FLAG_STOPPED = 8               /* zero twist returned                   (srv.py:374-377) */
+  NEOMPC_FLAG_STOPPED = 8,              /* zero twist returned                   (srv.py:374-377) */
+  NEOMPC_FLAG_NO_STATE = 16             /* instance_id beyond the reserved rows: solved as a cold start (see neompc_reserve_instances) */
 };
 
 /* Optimizer response (output_vel.twist.linear.x/.y, .angular.z; cpp:252, srv.py:375-377,389-391) + diagnostics. 32 bytes. */
@@ -191,7 +194,15 @@ int neompc_set_costmap_device(neompc_handle* h, const uint8_t* d_cells, uint32_t
 int neompc_set_footprint(neompc_handle* h, const float* xy, int n_vertices);
 
 /* ---- per-instance state (srv.py:115-117,136,138,146-149: initial_guess, last_control, waiting_time, collision,
- *      collision_footprint, old_goal) ---------------------------------------------------------------------- */
+ *      collision_footprint, old_goal) ----------------------------------------------------------------------
+ * neompc_request.instance_id names the state row of a robot; rows exist after neompc_reserve_instances(n) for ids 0..n-1.
+ *  - An id beyond the reserved rows is NOT silently accepted: the request is solved as a cold start, its response carries
+ *    NEOMPC_FLAG_NO_STATE, and the host-buffer entry points (neompc_solve_batch, neompc_solve_msgs) return NEOMPC_ERR_STATE
+ *    after writing the responses.
+ *  - Ids must be UNIQUE within one batch: two requests with the same id read and write the same row concurrently (the later
+ *    writer wins, nothing is reported).  With the environment variable NEOMPC_DEBUG_IDS=1 the host-buffer entry points
+ *    check this on the host (slow) and return NEOMPC_ERR_INVALID.
+ * Every call makes the handle's device current for its duration and restores the caller's current device on return. */
 int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances);
 int neompc_reset_state(neompc_handle* h, const uint32_t* ids, size_t n);     /* ids == NULL: all */
 /* Test/inspection hook: copies one instance's state to the host.  initial_guess: 3*control_steps floats. */
@@ -258,7 +269,7 @@ int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* c
                                  neompc_carrot_info* d_info_out, void* stream);
 
 /* ---- the step after the solve: the predicted path -------------------------------- */
-/* One pose of the nav_msgs/Path the reference publishes on "/mpc_local_plan" (publishLocalPlan, srv.py:271-310):
+/* One pose of the nav_msgs/Path the reference publishes on "local_plan" (srv.py:107; publishLocalPlan, srv.py:271-310):
  * position x, y and the orientation quaternion_from_euler(0, 0, yaw) (srv.py:182-196; x = y = 0).  32 bytes. */
 typedef struct neompc_plan_pose {
   double x, y;

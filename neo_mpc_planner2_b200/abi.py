@@ -111,6 +111,7 @@ PARAMS_DTYPE = np.dtype(PARAMS_FIELDS, align=False)
 assert PARAMS_DTYPE.itemsize == 128
 
 REFERENCE_PARAM_NAMES = [f[0] for f in PARAMS_FIELDS[:22]]
+KNOB_NAMES = [f[0] for f in PARAMS_FIELDS[22:] if f[0] != "reserved"]
 
 
 def params_record(params=None, **over) -> np.ndarray:
@@ -126,12 +127,19 @@ def params_record(params=None, **over) -> np.ndarray:
     rec = np.zeros((), dtype=PARAMS_DTYPE)
     src = {}
     if params is not None:
-        src = params if isinstance(params, dict) else {
-            k: getattr(params, k) for k in REFERENCE_PARAM_NAMES if hasattr(params, k)}
+        if isinstance(params, dict):
+            src = params
+        elif isinstance(params, np.ndarray) and params.dtype.names:
+            src = {k: params[k].item() for k in params.dtype.names if k != "reserved"}
+        else:
+            src = {k: getattr(params, k) for k in KNOB_NAMES + REFERENCE_PARAM_NAMES if hasattr(params, k)}
+    unknown = [k for k in list(src) + list(over) if k not in REFERENCE_PARAM_NAMES and k not in KNOB_NAMES]
+    if unknown:
+        raise KeyError(f"unknown neompc_params field(s): {unknown}")
     for name in REFERENCE_PARAM_NAMES:
         rec[name] = over.pop(name, src.get(name, defaults[name]))
-    for k, v in over.items():
-        rec[k] = v
+    for name in KNOB_NAMES:                      # solver knobs travel with the record (0 = library default)
+        rec[name] = over.pop(name, src.get(name, 0))
     return rec
 
 

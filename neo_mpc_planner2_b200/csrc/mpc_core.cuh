@@ -99,6 +99,7 @@ struct SolverConst {
   float* state;
   int state_stride;       // floats per row
   unsigned state_rows;
+  unsigned* err_word;     // set to 1 by any instance whose state row does not exist (nullptr: not reported)
 };
 
 // tables derived from (encoding, w_costmap, N): lut_cost[b] = w_costmap * c^2 / N  (srv.py:247,260); a lethal cell
@@ -395,11 +396,13 @@ struct Carry {
   bool latched;          // self.collision                     (srv.py:338-339)
   bool new_goal;         // goal_pose != old_goal              (srv.py:358-361)
   bool stateful;
+  bool no_state;         // a state row was asked for that does not exist (id beyond neompc_reserve_instances)
 };
 
 NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool valid) {
   Carry c;
   c.stateful = valid && rq.instance_id != NEOMPC_STATELESS && P.state != nullptr && rq.instance_id < P.state_rows;
+  c.no_state = valid && rq.instance_id != NEOMPC_STATELESS && !c.stateful;
   c.last[0] = c.last[1] = c.last[2] = 0.0f;
   c.waiting = 0.0f;
   c.latched = false;
@@ -1190,6 +1193,7 @@ struct Solver {
     if (collision) flags |= NEOMPC_FLAG_COLLISION;
     if (fp_hit) flags |= NEOMPC_FLAG_COLLISION_FOOTPRINT;
     if (new_goal) flags |= NEOMPC_FLAG_NEW_GOAL;
+    if (cr.no_state) flags |= NEOMPC_FLAG_NO_STATE;          // solved as a cold start; the host entry points return NEOMPC_ERR_STATE
     if (!valid) return;
     // ---- state: last_control (srv.py:393-395), warm start (srv.py:397-400), old_goal (srv.py:402)
     if (stateful) {
@@ -1220,6 +1224,7 @@ struct Solver {
       rs.cost = j_true;
       rs.iters = iters; rs.evals = evals; rs.status = status; rs.flags = flags;
       *resp = rs;
+      if (cr.no_state && P.err_word != nullptr) *P.err_word = 1u;
       if (twist != nullptr) { twist[0] = o[0]; twist[1] = o[1]; twist[2] = o[2]; }
     }
   }

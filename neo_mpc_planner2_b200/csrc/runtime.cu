@@ -3,6 +3,7 @@
 // and MpcOptimizationServer.optimizer (reference neo_mpc_planner2/mpc_optimization_server.py:349-403).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +45,8 @@ struct neompc_handle {
   neompc_optimizer_request* d_msgs = nullptr;
   size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
   uint64_t launches = 0;
+  unsigned* err_word = nullptr;     // mapped pinned word the kernels set when a request names a missing state row
+  bool debug_ids = false;           // NEOMPC_DEBUG_IDS=1: host-side uniqueness check of instance ids (slow)
   // carrot selection (row N2): shared global plan, byte -> raw-cost table, staging
   double* d_path = nullptr;
   size_t path_len = 0, path_cap = 0;
@@ -67,6 +70,20 @@ constexpr size_t kMailboxRequests = 64;
 static thread_local std::string g_create_error;
 
 namespace {
+
+// makes the handle's device current for the duration of an API call and restores the caller's afterwards
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define NEOMPC_DEVICE(h)                                                        \
+  DeviceGuard guard__((h)->device);                                             \
+  if (guard__.err != cudaSuccess) return cuda_fail(h, guard__.err, "cudaSetDevice")
 
 int fail(neompc_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -118,6 +135,7 @@ void rebuild_const(neompc_handle* h) {
   h->c.cm_scale = 1.0f / (float)h->c.lethal_byte;
   h->c.state = h->d_state;
   h->c.state_rows = h->state_rows;
+  h->c.err_word = h->err_word;
   choose_tiling(h->params.control_steps, h->params.lanes_per_instance, &h->G, &h->S);
   h->Gl = h->G; h->Sl = h->S;
   if (h->params.lanes_per_instance <= 0) choose_latency_tiling(h->params.control_steps, &h->Gl, &h->Sl);
@@ -251,6 +269,29 @@ int rebuild_corner_map(neompc_handle* h) {
   return NEOMPC_OK;
 }
 
+// after a host-buffer solve has been synchronised: did a request name a state row that does not exist?
+int check_state_errors(neompc_handle* h) {
+  if (*h->err_word == 0u) return NEOMPC_OK;
+  *h->err_word = 0u;
+  return fail(h, NEOMPC_ERR_STATE,
+              "a request's instance_id lies beyond the reserved state rows (neompc_reserve_instances); it was solved as a "
+              "cold start and its response carries NEOMPC_FLAG_NO_STATE");
+}
+
+// NEOMPC_DEBUG_IDS=1: instance ids of one batch must be unique (two requests with one id race on its state row)
+template <class Rec>
+int check_unique_ids(neompc_handle* h, const Rec* recs, size_t n) {
+  if (!h->debug_ids) return NEOMPC_OK;
+  std::vector<uint32_t> ids;
+  ids.reserve(n);
+  for (size_t i = 0; i < n; ++i)
+    if (recs[i].instance_id != NEOMPC_STATELESS) ids.push_back(recs[i].instance_id);
+  std::sort(ids.begin(), ids.end());
+  if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
+    return fail(h, NEOMPC_ERR_INVALID, "duplicate instance_id within one batch (NEOMPC_DEBUG_IDS check)");
+  return NEOMPC_OK;
+}
+
 int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
                     float* d_twist, float* d_plan, cudaStream_t s, size_t tiling_n = 0) {
   if (n == 0) return NEOMPC_OK;
@@ -320,13 +361,17 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
       return NEOMPC_ERR_CUDA;                                                               \
     }                                                                                       \
   } while (0)
-  CREATE_CUDA(cudaSetDevice(device));
+  DeviceGuard guard__(device);
+  CREATE_CUDA(guard__.err);
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CREATE_CUDA(cudaMalloc(&h->d_raw_table, 256));
   CREATE_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   CREATE_CUDA(cudaMalloc(&h->d_lut_cost, kTableSize * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&h->d_lut_flag, kTableSize + 6));
+  CREATE_CUDA(cudaHostAlloc(&h->err_word, sizeof(unsigned), cudaHostAllocMapped));
+  *h->err_word = 0u;
+  h->debug_ids = std::getenv("NEOMPC_DEBUG_IDS") != nullptr;
   CREATE_CUDA(cudaHostAlloc(&h->mb_msgs, kMailboxRequests * sizeof(neompc_optimizer_request), cudaHostAllocMapped));
   CREATE_CUDA(cudaHostAlloc(&h->mb_reqs, kMailboxRequests * sizeof(neompc_request), cudaHostAllocMapped));
   CREATE_CUDA(cudaHostAlloc(&h->mb_resp, kMailboxRequests * sizeof(neompc_response), cudaHostAllocMapped));
@@ -342,13 +387,13 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
 
 int neompc_destroy(neompc_handle* h) {
   if (!h) return NEOMPC_OK;
-  if (h->device >= 0) cudaSetDevice(h->device);
+  DeviceGuard guard__(h->device >= 0 ? h->device : 0);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_cells4); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
-  cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan);
+  cudaFreeHost(h->err_word); cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan);
   delete h;
   return NEOMPC_OK;
 }
@@ -357,7 +402,7 @@ int neompc_set_params(neompc_handle* h, const neompc_params* params) {
   if (!h || !params) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   std::string err;
   if (!validate_params(*params, err)) return fail(h, NEOMPC_ERR_INVALID, err);
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   const bool steps_changed = params->control_steps != h->params.control_steps;
   h->params = *params;
   if (steps_changed && h->d_state) {           // rows have a different layout now: start over (srv.py never resizes either)
@@ -385,7 +430,7 @@ int neompc_get_params(const neompc_handle* h, neompc_params* out) {
 static int set_costmap_common(neompc_handle* h, const uint8_t* cells, bool on_device, uint32_t width, uint32_t height,
                               double resolution, double origin_x, double origin_y, int encoding) {
   if (!h) return NEOMPC_ERR_INVALID;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   if (encoding != NEOMPC_ENC_OCCUPANCY && encoding != NEOMPC_ENC_NAV2_RAW)
     return fail(h, NEOMPC_ERR_INVALID, "unknown costmap encoding");
   if (cells == nullptr) {                      // free space
@@ -444,7 +489,7 @@ int neompc_set_footprint(neompc_handle* h, const float* xy, int n_vertices) {
 
 int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances) {
   if (!h) return NEOMPC_ERR_INVALID;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   if (n_instances <= h->state_rows) return NEOMPC_OK;
   const int stride = state_stride_for(h->params.control_steps);
   float* fresh = nullptr;
@@ -466,7 +511,7 @@ int neompc_reserve_instances(neompc_handle* h, uint32_t n_instances) {
 
 int neompc_reset_state(neompc_handle* h, const uint32_t* ids, size_t n) {
   if (!h) return NEOMPC_ERR_INVALID;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   if (!h->d_state) return NEOMPC_OK;
   const int stride = h->c.state_stride;
   if (ids == nullptr) {
@@ -492,7 +537,7 @@ int neompc_get_state(neompc_handle* h, uint32_t id, float* initial_guess, float 
                      uint32_t* flags) {
   if (!h) return NEOMPC_ERR_INVALID;
   if (id >= h->state_rows) return fail(h, NEOMPC_ERR_STATE, "instance id beyond reserved capacity");
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   const int stride = h->c.state_stride;
   std::vector<float> row(stride);
   NEOMPC_CUDA(h, cudaMemcpyAsync(row.data(), h->d_state + (size_t)id * stride, stride * sizeof(float),
@@ -510,7 +555,7 @@ int neompc_get_state(neompc_handle* h, uint32_t id, float* initial_guess, float 
 int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
                               float* d_twist_or_null, float* d_plan_or_null, void* stream) {
   if (!h || (n > 0 && (!d_reqs || !d_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   return do_solve_device(h, d_reqs, n, d_out, d_twist_or_null, d_plan_or_null, s);
 }
@@ -519,8 +564,10 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
                        float* plan_or_null) {
   if (!h || (n > 0 && (!reqs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
-  int rc = ensure_staging(h, n, plan_or_null != nullptr, false);
+  NEOMPC_DEVICE(h);
+  int rc = check_unique_ids(h, reqs, n);
+  if (rc != NEOMPC_OK) return rc;
+  rc = ensure_staging(h, n, plan_or_null != nullptr, false);
   if (rc != NEOMPC_OK) return rc;
   if (n <= kMailboxRequests) {                 // small batch: pinned mailbox in, mapped mailbox out (see solve_msgs)
     const size_t n3s = n * 3 * (size_t)h->params.control_steps;
@@ -531,7 +578,7 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
     NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
     std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
     if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3s * sizeof(float));
-    return NEOMPC_OK;
+    return check_state_errors(h);
   }
   // Large batches are cut into two chunks on two streams, so the H2D copy of one chunk, the solve of
   // the other and the D2H copies overlap (the copy engines for the two directions and the SMs are independent).
@@ -558,14 +605,14 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
   }
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   if (chunks > 1) NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream2));
-  return NEOMPC_OK;
+  return check_state_errors(h);
 }
 
 int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n, neompc_request* d_reqs,
                          void* stream) {
   if (!h || (n > 0 && (!d_msgs || !d_reqs))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_msgs, (unsigned)n, d_reqs);
   NEOMPC_CUDA(h, cudaGetLastError());
@@ -577,8 +624,10 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
                       float* plan_or_null) {
   if (!h || (n > 0 && (!msgs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
-  int rc = ensure_staging(h, n, plan_or_null != nullptr, true);
+  NEOMPC_DEVICE(h);
+  int rc = check_unique_ids(h, msgs, n);
+  if (rc != NEOMPC_OK) return rc;
+  rc = ensure_staging(h, n, plan_or_null != nullptr, true);
   if (rc != NEOMPC_OK) return rc;
   if (n <= kMailboxRequests) {
     // controller-tick path: messages go through the mapped mailbox (the pack kernel reads them over PCIe), responses
@@ -592,7 +641,7 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
     NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
     std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
     if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3 * sizeof(float));
-    return NEOMPC_OK;
+    return check_state_errors(h);
   }
   NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_msgs, msgs, n * sizeof(neompc_optimizer_request), cudaMemcpyHostToDevice, h->stream));
   rc = neompc_pack_requests(h, h->d_msgs, n, h->d_reqs, h->stream);
@@ -604,14 +653,14 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
     NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null, h->d_plan, n * 3 * (size_t)h->params.control_steps * sizeof(float),
                                    cudaMemcpyDeviceToHost, h->stream));
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
-  return NEOMPC_OK;
+  return check_state_errors(h);
 }
 
 int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const float* u, size_t n, float* J,
                           float* grad_or_null) {
   if (!h || (n > 0 && (!reqs || !u || !J))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   const size_t n3 = n * 3 * (size_t)h->params.control_steps;
   int rc = ensure_staging(h, n, true, false);
   if (rc != NEOMPC_OK) return rc;
@@ -640,7 +689,7 @@ int neompc_local_plan_device(neompc_handle* h, const neompc_request* d_reqs, con
   if (!h || (n > 0 && (!d_reqs || !d_plan || !d_poses_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
   if (n > 0xffffffffu) return fail(h, NEOMPC_ERR_INVALID, "batch too large");
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   const int N = h->params.control_steps;
   // self.dt = prediction_horizon / no_ctrl_steps (srv.py:137), in float64 like the reference
   const double dt = (double)h->params.prediction_horizon / (double)N;
@@ -655,7 +704,7 @@ int neompc_local_plan(neompc_handle* h, const neompc_request* reqs, const float*
                       neompc_plan_pose* poses_out) {
   if (!h || (n > 0 && (!reqs || !plan || !poses_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   const size_t N = (size_t)h->params.control_steps;
   int rc = ensure_staging(h, n, true, false);
   if (rc != NEOMPC_OK) return rc;
@@ -676,7 +725,7 @@ int neompc_local_plan(neompc_handle* h, const neompc_request* reqs, const float*
 
 int neompc_set_plan(neompc_handle* h, const double* xyyaw, size_t n_poses) {
   if (!h || !xyyaw || n_poses == 0 || n_poses > 0x7fffffffu) return fail(h, NEOMPC_ERR_INVALID, "plan must have >= 1 pose");
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   if (n_poses > h->path_cap) {
     NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->d_path) cudaFree(h->d_path);
@@ -697,7 +746,7 @@ int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* c
   if (h->path_len == 0) return fail(h, NEOMPC_ERR_INVALID, "no plan set (neompc_set_plan)");
   if (!(cp->controller_frequency > 0.0f)) return fail(h, NEOMPC_ERR_INVALID, "controller_frequency must be > 0");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   CarrotConst c{};
   c.plan = h->d_path;
   c.L = (unsigned)h->path_len;
@@ -726,7 +775,7 @@ int neompc_build_requests(neompc_handle* h, const neompc_carrot_params* cp, cons
                           uint32_t first_instance_id, neompc_request* reqs_out, neompc_carrot_info* info_out) {
   if (!h || !cp || (n > 0 && (!ticks || !reqs_out || !info_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
   if (n == 0) return NEOMPC_OK;
-  NEOMPC_CUDA(h, cudaSetDevice(h->device));
+  NEOMPC_DEVICE(h);
   int rc = ensure_staging(h, n, false, false);
   if (rc != NEOMPC_OK) return rc;
   if (n > h->cap_ticks) {

@@ -10,7 +10,12 @@ stack keeps working without touching the plugin: only the Python executable is s
   * publisher 'local_plan' (nav_msgs/Path, the predicted path)                       srv.py:107, :271-310
   * subscription '/local_costmap/published_footprint' (geometry_msgs/PolygonStamped) srv.py:140-144, :154-155
   * the costmap: the reference reads it through neo_nav2_py_costmap2D's Costmap2d(self) (srv.py:118); here the
-    node subscribes to the OccupancyGrid nav2 publishes on '/local_costmap/costmap'
+    node subscribes to the OccupancyGrid nav2 publishes on '/local_costmap/costmap' AND to the
+    map_msgs/OccupancyGridUpdate patches on '/local_costmap/costmap_updates' (with nav2's default
+    always_send_full_costmap: false only patches are sent while the costmap's origin stands still — e.g. while the
+    robot waits out a collision stop, srv.py:374-382 — so ignoring them would freeze the obstacle picture)
+  * until BOTH a costmap and a footprint have arrived the handler answers with a zero twist instead of solving in free
+    space (the reference cannot solve without its Costmap2d either, and objective() crashes without self.footprint)
   * dynamic parameters                                                               srv.py:405-439
 
 ``rclpy``, ``neo_srvs2`` and the message packages are imported when this module is imported; they are not part of this
@@ -32,6 +37,10 @@ from rclpy.parameter import Parameter
 from rcl_interfaces.msg import SetParametersResult
 from geometry_msgs.msg import PolygonStamped, PoseStamped
 from nav_msgs.msg import OccupancyGrid, Path
+try:                                      # map_msgs ships with nav2; the stand-in test modules provide it too
+    from map_msgs.msg import OccupancyGridUpdate
+except ImportError:                       # pragma: no cover
+    OccupancyGridUpdate = None
 from neo_srvs2.srv import Optimizer
 
 from .abi import ENC_OCCUPANCY, REQUEST_DTYPE
@@ -78,6 +87,13 @@ class MpcOptimizationServer(Node):
             PolygonStamped, '/local_costmap/published_footprint', self.footprint_callback, 10)   # srv.py:140-144
         self.subscription_costmap = self.create_subscription(
             OccupancyGrid, '/local_costmap/costmap', self.costmap_callback, 10)  # stands for Costmap2d(self), srv.py:118
+        self.subscription_costmap_updates = None
+        if OccupancyGridUpdate is not None:
+            self.subscription_costmap_updates = self.create_subscription(
+                OccupancyGridUpdate, '/local_costmap/costmap_updates', self.costmap_update_callback, 10)
+        self._grid = None                                                        # cached cells of the last full costmap
+        self._grid_info = None
+        self.costmap_generation = 0
         self.last_time = 0.0                                                     # srv.py:138
         self.last_response = None
         self.solution = None
@@ -88,8 +104,26 @@ class MpcOptimizationServer(Node):
 
     def costmap_callback(self, msg):
         info = msg.info
-        cells = np.asarray(msg.data, dtype=np.int8).reshape(info.height, info.width)
-        self._solver.set_costmap(cells, info.resolution, info.origin.position.x, info.origin.position.y, ENC_OCCUPANCY)
+        self._grid = np.array(msg.data, dtype=np.int8).reshape(info.height, info.width)
+        self._grid_info = (info.resolution, info.origin.position.x, info.origin.position.y)
+        self._upload_costmap()
+
+    def costmap_update_callback(self, msg):
+        """map_msgs/OccupancyGridUpdate: a rectangular patch (x, y, width, height, data) of the last full grid."""
+        if self._grid is None:
+            return                                                               # no full grid yet: nothing to patch
+        h, w = self._grid.shape
+        x0, y0, pw, ph = int(msg.x), int(msg.y), int(msg.width), int(msg.height)
+        if x0 < 0 or y0 < 0 or x0 + pw > w or y0 + ph > h or pw * ph != len(msg.data):
+            self.get_logger().warn("costmap update outside the cached grid: ignored until the next full costmap")
+            return
+        self._grid[y0:y0 + ph, x0:x0 + pw] = np.asarray(msg.data, dtype=np.int8).reshape(ph, pw)
+        self._upload_costmap()
+
+    def _upload_costmap(self):
+        res, ox, oy = self._grid_info
+        self._solver.set_costmap(self._grid, res, ox, oy, ENC_OCCUPANCY)
+        self.costmap_generation += 1
 
     def _place_footprint(self, pose):
         """The library takes the polygon in the robot frame and places it at the request's current pose; the reference
@@ -110,6 +144,13 @@ class MpcOptimizationServer(Node):
         current_time = time.time()                                               # srv.py:369-371
         delta_t = current_time - self.last_time
         self.last_time = current_time
+        if self._grid is None or self.footprint is None or not self.footprint.points:
+            # no obstacle picture yet: standing still is the only safe answer (nothing is solved in free space)
+            self.get_logger().warn("optimizer called before a costmap and a footprint were received: zero twist")
+            response.output_vel.twist.linear.x = 0.0
+            response.output_vel.twist.linear.y = 0.0
+            response.output_vel.twist.angular.z = 0.0
+            return response
         self._place_footprint(request.current_pose.pose)
         msg = request_to_msg(request, delta_t, instance_id=0)
         out, plan = self._solver.solve_msgs(msg, want_plan=True)

@@ -57,11 +57,18 @@ class BatchSolver:
 
     # ------------------------------------------------------------------ environment
     def set_params(self, params=None, **over):
-        rec = params_record(params if params is not None else
-                            {k: self.params[k].item() for k in self.params.dtype.names if k != "reserved"}, **over)
+        """neompc_set_params.  Without `params` the CURRENT record is the starting point: every field that is not named —
+        solver knobs included — keeps its value."""
+        rec = params_record(self.params if params is None else params, **over)
         self._check(self._lib.neompc_set_params(self._h, _ptr(rec)), "neompc_set_params")
         self.params = rec
         self.control_steps = int(rec["control_steps"])
+
+    def get_params(self):
+        """The record the library holds (neompc_get_params)."""
+        rec = np.zeros((), dtype=PARAMS_DTYPE)
+        self._check(self._lib.neompc_get_params(self._h, _ptr(rec)), "neompc_get_params")
+        return rec
 
     def set_costmap(self, cells, resolution, origin_x, origin_y, encoding=ENC_OCCUPANCY):
         if cells is None:

@@ -121,6 +121,16 @@ class Optimizer:
 
 
 @dataclass
+class OccupancyGridUpdate:
+    header: Header = field(default_factory=Header)
+    x: int = 0
+    y: int = 0
+    width: int = 0
+    height: int = 0
+    data: list = field(default_factory=list)
+
+
+@dataclass
 class SetParametersResult:
     successful: bool = True
     reason: str = ""
@@ -236,6 +246,8 @@ def install():
          Polygon=Polygon, PolygonStamped=PolygonStamped, Twist=Twist, Point32=Point32)
     _mod("nav_msgs")
     _mod("nav_msgs.msg", OccupancyGrid=OccupancyGrid, Path=Path)
+    _mod("map_msgs")
+    _mod("map_msgs.msg", OccupancyGridUpdate=OccupancyGridUpdate)
     _mod("neo_nav2_py_costmap2D")
     _mod("neo_nav2_py_costmap2D.line_iterator", LineIterator=object)
     _mod("neo_nav2_py_costmap2D.costmap", Costmap2d=_PlaceholderCostmap)

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from neo_mpc_planner2_b200 import _lib, abi
@@ -82,3 +83,20 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "scipy.optimize" not in src, f
+
+
+def test_params_record_keeps_solver_knobs():
+    """A record rebuilt from a record (what BatchSolver.set_params(**changes) does) keeps every field that is not named —
+    the solver knobs included (round-1 advisor finding: they were reset to 0)."""
+    rec = abi.params_record(abi.README_SAMPLE, footprint_mode=abi.FOOTPRINT_MOVING, costmap_mode=abi.COSTMAP_BILINEAR,
+                            lbfgs_memory=3, control_smoothing=0.005, max_iterations=50, lanes_per_instance=8,
+                            costmap_guidance=abi.GUIDANCE_OFF)
+    again = abi.params_record(rec, w_trans=0.3)
+    assert again["w_trans"] == np.float32(0.3)
+    for k in abi.KNOB_NAMES:
+        assert again[k] == rec[k], k
+    for k in abi.REFERENCE_PARAM_NAMES:
+        if k != "w_trans":
+            assert again[k] == rec[k], k
+    with pytest.raises(KeyError):
+        abi.params_record(abi.README_SAMPLE, w_tranz=1.0)

@@ -564,3 +564,51 @@ def test_errors(Solver):
             s.get_state(5)
         with pytest.raises(NeompcError):
             s.set_params(dict(control_steps=3, max_vel_trans=-1.0))
+
+
+def test_set_params_keeps_solver_knobs(Solver):
+    """BatchSolver.set_params(**changes) starts from the current record: a dynamic parameter change does not switch the
+    objective mode or any other solver knob back to its default (read back through neompc_get_params)."""
+    from neo_mpc_planner2_b200 import abi
+    wl, p, cm = setup_workload("c2", 64, 3)
+    with Solver(wl.params, footprint_mode=abi.FOOTPRINT_MOVING, costmap_mode=abi.COSTMAP_BILINEAR, lbfgs_memory=3,
+                control_smoothing=0.005, costmap_guidance=abi.GUIDANCE_OFF) as s:
+        s.set_params(w_trans=0.3)
+        got = s.get_params()
+        assert got["w_trans"] == np.float32(0.3) and got["w_orient"] == np.float32(wl.params["w_orient"])
+        assert got["footprint_mode"] == abi.FOOTPRINT_MOVING and got["costmap_mode"] == abi.COSTMAP_BILINEAR
+        assert got["lbfgs_memory"] == 3 and got["control_smoothing"] == np.float32(0.005)
+        assert got["costmap_guidance"] == abi.GUIDANCE_OFF
+
+
+def test_missing_state_row_is_reported(Solver):
+    """An instance_id beyond the reserved rows: NEOMPC_ERR_STATE from the host-buffer entry point, NEOMPC_FLAG_NO_STATE in the
+    response, and the request is still solved (as a cold start)."""
+    from neo_mpc_planner2_b200.solver import NeompcError
+    wl, p, cm = setup_workload("c2", 128, 3)
+    req = wl.requests.copy()
+    req["instance_id"] = np.arange(len(req), dtype=np.uint32)
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        s.reserve_instances(100)
+        out = np.zeros(len(req), dtype=s.solve(req[:1]).dtype)
+        with pytest.raises(NeompcError, match="reserved state rows"):
+            s.solve(req, out=out)
+        assert not (out["flags"][:100] & 16).any() and (out["flags"][100:] & 16).all()
+        assert np.isfinite(out["cost"]).all() and (out["iters"] > 0).all()
+        s.reset_state()
+        ok = s.solve(req[:100])                                       # all rows exist: no error
+        assert not (ok["flags"] & 16).any()
+
+
+def test_duplicate_instance_ids_debug_check(Solver, monkeypatch):
+    from neo_mpc_planner2_b200.solver import NeompcError
+    wl, p, cm = setup_workload("c2", 64, 3)
+    req = wl.requests.copy()
+    req["instance_id"] = 5
+    monkeypatch.setenv("NEOMPC_DEBUG_IDS", "1")
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        s.reserve_instances(8)
+        with pytest.raises(NeompcError, match="duplicate instance_id"):
+            s.solve(req)

@@ -92,14 +92,25 @@ def test_node_answers_like_the_library(ros):
     finally:
         ros.Node.create_service = orig_service
     assert created["service"][0] is ros.Optimizer and created["service"][1] == "optimizer"
-    assert set(subs) == {"/local_costmap/published_footprint", "/local_costmap/costmap"}
+    assert set(subs) == {"/local_costmap/published_footprint", "/local_costmap/costmap", "/local_costmap/costmap_updates"}
     node.PubRaysPath = Recorder()
-    # costmap and footprint arrive on their topics
+    # before a costmap and a footprint have arrived the node stands still instead of solving in free space
+    early = created["service"][2](make_request(ros, wl.requests[0]), ros.OptimizerResponse())
+    assert (early.output_vel.twist.linear.x, early.output_vel.twist.linear.y, early.output_vel.twist.angular.z) == (0.0, 0.0, 0.0)
+    assert node.PubRaysPath.msgs == []
+    # costmap and footprint arrive on their topics: first an EMPTY full grid, then the obstacles as update patches (what
+    # nav2 sends while the costmap origin stands still, always_send_full_costmap: false)
     grid = types.SimpleNamespace(
         info=types.SimpleNamespace(width=wl.cells.shape[1], height=wl.cells.shape[0], resolution=wl.resolution,
                                    origin=types.SimpleNamespace(position=types.SimpleNamespace(x=wl.origin_x, y=wl.origin_y))),
-        data=wl.cells.astype(np.int8).ravel().tolist())
+        data=np.zeros(wl.cells.size, np.int8).tolist())
     subs["/local_costmap/costmap"](grid)
+    H, W = wl.cells.shape
+    for (y0, x0) in ((0, 0), (0, W // 2), (H // 2, 0), (H // 2, W // 2)):
+        patch = wl.cells[y0:y0 + H // 2, x0:x0 + W // 2].astype(np.int8)
+        subs["/local_costmap/costmap_updates"](ros.OccupancyGridUpdate(x=x0, y=y0, width=patch.shape[1], height=patch.shape[0],
+                                                                       data=patch.ravel().tolist()))
+    assert node.costmap_generation == 5 and np.array_equal(node._grid.view(np.uint8), wl.cells)
     p = oracle.MpcParams(**wl.params)
     with BatchSolver(wl.params) as direct:
         direct.load_workload(wl)
