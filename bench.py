@@ -241,8 +241,17 @@ def run_ours(args):
     wl = workloads.config(args.config, batch=per_gpu, seed=None if rank == 0 else 1000 + rank)
     n = wl.batch
     n_steps = wl.control_steps
-    solver = BatchSolver(wl.params, device=local, lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode,
-                         costmap_mode=args.costmap_mode, costmap_guidance=args.costmap_guidance)
+    knobs = dict(lanes_per_instance=args.lanes, footprint_mode=args.footprint_mode, costmap_mode=args.costmap_mode,
+                 costmap_guidance=args.costmap_guidance)
+    fleet = None
+    if world > 1:
+        # one rank of a fleet: the sharding and the single collective (NCCL all-gather of the solved twists, enqueued by
+        # the library behind its solve kernel) are libneompc's own (include/neompc.h "multi-GPU")
+        from neo_mpc_planner2_b200.fleet import FleetSolver
+        fleet = FleetSolver(wl.params, device=local, **knobs)
+        solver = fleet.solver
+    else:
+        solver = BatchSolver(wl.params, device=local, **knobs)
     solver.load_workload(wl)
     G, S = solver.tiling
 
@@ -250,27 +259,24 @@ def run_ours(args):
     resp_host = torch.empty((n, RESPONSE_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
     d_reqs = req_host.to(dev)
     d_out = torch.empty((n, RESPONSE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    d_twist = [torch.empty((n, 3), dtype=torch.float32, device=dev) for _ in range(2)]     # double-buffered gather payload
-    d_all = torch.empty((world * n, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    # the gather payload / result, double-buffered: [world * n, 3], this rank's rows are [rank * n, (rank + 1) * n)
+    d_all = [torch.zeros((world * n, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    all_host = torch.empty((world * n, 3), dtype=torch.float32).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(dev)              # solve kernel + all timing events
-    comm = torch.cuda.Stream(dev) if world > 1 else None     # the NCCL all-gather of the previous step's twists
     torch.cuda.set_stream(stream)
-    kdone = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def launch_kernel(k, k_ev=None):
+    def launch_step(k, k_ev=None):
+        """Solve kernel of step k on `stream`; with N > 1 the library also enqueues the all-gather of step k on its own
+        communication stream behind the kernel."""
         if k_ev is not None:
             k_ev[0].record(stream)
-        solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_twist[k & 1].data_ptr(), None, stream.cuda_stream)
+        if world > 1:
+            solver.solve_gather_device(d_reqs.data_ptr(), n, n, d_out.data_ptr(), d_all[k & 1].data_ptr(), stream.cuda_stream)
+        else:
+            solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_all[k & 1].data_ptr(), None, stream.cuda_stream)
         if k_ev is not None:
-            k_ev[1].record(stream)
-        kdone[k & 1].record(stream)
-
-    def launch_gather(k):
-        """The single collective of the path: all ranks' (vx, vy, omega) of step k, enqueued behind kernel k only."""
-        with torch.cuda.stream(comm):
-            comm.wait_event(kdone[k & 1])
-            dist.all_gather_into_tensor(d_all, d_twist[k & 1])
+            k_ev[1].record(stream)               # (brackets the kernel only: the gather is on the other stream)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -280,10 +286,9 @@ def run_ours(args):
 
     for k in range(max(args.warmup, 3)):
         flush.fill_(1)
-        launch_kernel(k)
+        launch_step(k)
         if world > 1:
-            launch_gather(k)
-            stream.wait_stream(comm)
+            solver.gather_wait(stream.cuda_stream, 0)
     barrier()
 
     sampler = ClockSampler(local)
@@ -293,22 +298,19 @@ def run_ours(args):
             torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     barrier()
     # A timed step = one solve kernel + one all-gather.  With N > 1 the step is software-pipelined: the gather of step
-    # k-1 (which depends on kernel k-1 only) is enqueued first and runs on its own stream while kernel k computes; the
-    # bracket closes when both are done.  A last bracket drains the gather of the final step, so K kernels and K
-    # gathers are inside timed regions; the L2 flush between steps is outside them.
+    # k-1 (which depends on kernel k-1 only) runs on the library's communication stream while kernel k computes; the
+    # bracket of step k closes when kernel k AND gather k-1 are done.  A last bracket drains the gather of the final step,
+    # so K kernels and K gathers are inside timed regions; the L2 flush between steps is outside them.
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                                    # L2 flush between timed iterations (untimed)
         evs[k][0].record(stream)
+        launch_step(k, (evs[k][2], evs[k][3]))
         if world > 1 and k > 0:
-            launch_gather(k - 1)
-        launch_kernel(k, (evs[k][2], evs[k][3]))
-        if world > 1 and k > 0:
-            stream.wait_stream(comm)
+            solver.gather_wait(stream.cuda_stream, 1)            # the gather before the one just enqueued
         evs[k][1].record(stream)
     evs[args.steps][0].record(stream)
     if world > 1:
-        launch_gather(args.steps - 1)
-        stream.wait_stream(comm)
+        solver.gather_wait(stream.cuda_stream, 0)
     evs[args.steps][1].record(stream)
     barrier()
     launches = solver.launch_count - launches0
@@ -321,20 +323,65 @@ def run_ours(args):
     total_ms_max = float(t.item())
     value = world * n * args.steps / (total_ms_max * 1e-3)
 
-    # ---- e2e: host buffers through the C ABI (H2D + solve + D2H inside the timed region)
+    # ---- what was gathered is what was solved (untimed)
+    gather_check = None
+    if world > 1:
+        last = d_all[(args.steps - 1) & 1]
+        resp_dev = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESPONSE_DTYPE)
+        mine = np.stack([resp_dev["vx"], resp_dev["vy"], resp_dev["omega"]], axis=1)
+        own_ok = last[rank * n:(rank + 1) * n].cpu().numpy().tobytes() == mine.tobytes()
+        # every rank holds the same tensor: compare a position-weighted checksum of the raw bits across ranks
+        bits = last.view(torch.int32).to(torch.int64).flatten()
+        digest = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+        digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        same = all(bool((d == digests[0]).all()) for d in digests)
+        # and equal to ONE GPU solving the same requests: rank 0 re-solves the first rows of every rank's shard
+        kchk = min(n, 8192 // world)
+        head = [torch.zeros((kchk, REQUEST_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(head, d_reqs[:kchk].contiguous())
+        flags = torch.tensor([int(own_ok), int(same), 1], device=dev)
+        if rank == 0:
+            chk = BatchSolver(wl.params, device=local, **dict(knobs, lanes_per_instance=G))
+            chk.load_workload(wl)
+            reqs_all = np.frombuffer(torch.cat(head).cpu().numpy().tobytes(), dtype=REQUEST_DTYPE)
+            one = chk.solve(reqs_all)
+            chk.close()
+            one_tw = np.stack([one["vx"], one["vy"], one["omega"]], axis=1).reshape(world, kchk, 3)
+            got = last.view(world, n, 3)[:, :kchk].cpu().numpy()
+            flags[2] = int(got.tobytes() == one_tw.tobytes())
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        gather_check = {"own_rows_equal_own_responses": bool(flags[0]), "all_ranks_hold_the_same_tensor": bool(flags[1]),
+                        "equal_to_one_gpu_solve": bool(flags[2]), "rows_compared_with_one_gpu": int(world * kchk)}
+        assert all(bool(f) for f in flags), gather_check
+
+    # ---- e2e: host buffers (H2D + solve [+ gather] + D2H inside the timed region)
+    def e2e_step():
+        if world > 1:
+            d_reqs.copy_(req_host, non_blocking=True)                                   # H2D of this rank's shard
+            solver.solve_gather_device(d_reqs.data_ptr(), n, n, d_out.data_ptr(), d_all[0].data_ptr(), stream.cuda_stream)
+            solver.gather_wait(stream.cuda_stream, 0)
+            all_host.copy_(d_all[0], non_blocking=True)                                 # D2H of ALL ranks' twists
+            stream.synchronize()
+        else:
+            solver.solve_raw(req_host.data_ptr(), n, resp_host.data_ptr())
     for _ in range(2):
-        solver.solve_raw(req_host.data_ptr(), n, resp_host.data_ptr())
+        e2e_step()
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        solver.solve_raw(req_host.data_ptr(), n, resp_host.data_ptr())
+        e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t.item())
+    e2e_s = float(t.item())
+    e2e_value = world * n * e2e_steps / e2e_s
+    if world > 1:
+        resp_host.copy_(d_out)
+        torch.cuda.synchronize(dev)
     clocks = sampler.stop()
 
     # ---- sustained: >= 2 s of back-to-back solve kernels (no L2 flush, no host gaps) — does the flushed 20-step figure
@@ -347,7 +394,7 @@ def run_ours(args):
     barrier()
     s0.record(stream)
     for k in range(n_sus):
-        solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_twist[k & 1].data_ptr(), None, stream.cuda_stream)
+        solver.solve_device(d_reqs.data_ptr(), n, d_out.data_ptr(), d_all[k & 1].data_ptr(), None, stream.cuda_stream)
     s1.record(stream)
     barrier()
     sus_ms = s0.elapsed_time(s1)
@@ -421,9 +468,13 @@ def run_ours(args):
                          "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
                          "issue_slots": issue,
                          "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * REQUEST_DTYPE.itemsize),
-                    "d2h_bytes_per_step": int(n * RESPONSE_DTYPE.itemsize), "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "api": "neompc_solve_batch (pinned host buffers)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n * REQUEST_DTYPE.itemsize),
+                    "d2h_bytes_per_step": int(world * n * RESPONSE_DTYPE.itemsize) if world == 1 else int(world * world * n * 12),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "neompc_solve_batch (pinned host buffers)" if world == 1 else
+                           "per rank: H2D of its shard, neompc_solve_gather_device (solve + NCCL all-gather), D2H of all ranks' "
+                           "(vx,vy,omega); bytes are whole-job totals"},
+            "gather_check": gather_check,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "single_request_latency": lat,

@@ -67,7 +67,8 @@ enum {
   NEOMPC_ERR_INVALID = -1,     /* bad argument / parameter */
   NEOMPC_ERR_NO_DEVICE = -2,   /* no usable CUDA device (there is no CPU fallback) */
   NEOMPC_ERR_CUDA = -3,        /* a CUDA runtime call failed */
-  NEOMPC_ERR_STATE = -4        /* instance id beyond the reserved capacity */
+  NEOMPC_ERR_STATE = -4,       /* instance id beyond the reserved capacity */
+  NEOMPC_ERR_NCCL = -5         /* NCCL missing (it is bound at run time, libnccl.so.2) or an NCCL call failed */
 };
 
 /* costmap cell encodings (semantics declared in DESIGN.md "Costmap semantics"; the reference reads its
@@ -228,6 +229,39 @@ int neompc_solve_msgs(neompc_handle* h, const neompc_optimizer_request* msgs, si
 /* Device-side packing only (d_msgs, d_reqs device pointers), asynchronous on `stream`. */
 int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n,
                          neompc_request* d_reqs, void* stream);
+
+/* ---- multi-GPU: contiguous shards, ONE collective ------------------------------------------
+ * Problems are independent (the reference solves them one at a time, srv.py:349-403), so a batch of n requests is cut
+ * into n_ranks contiguous shards of neompc_shard_rows(n, n_ranks) = ceil(n / n_ranks) rows (the last one may be shorter);
+ * costmap, footprint and parameters are set on every handle (replicated, <= 16 MB); per-instance state lives on the
+ * handle that solves the request (a robot keeps its state as long as it keeps its position in the batch).  The only
+ * exchange is an NCCL all-gather of the solved (vx, vy, omega), 12 B per problem, after which every rank holds all of
+ * them.  NCCL is bound at run time (dlopen libnccl.so.2): a single-GPU user of this library does not need it.
+ * One handle = one GPU = one rank.  Two ways to form the communicator: */
+#define NEOMPC_COMM_ID_BYTES 128
+/* (a) one process per GPU (MPI / torchrun style): rank 0 creates an id, the caller distributes it, every rank joins. */
+int neompc_comm_unique_id(unsigned char id[NEOMPC_COMM_ID_BYTES]);
+int neompc_comm_init(neompc_handle* h, const unsigned char id[NEOMPC_COMM_ID_BYTES], int n_ranks, int rank);
+/* (b) one process driving several GPUs (a C++ fleet host): handles[i] becomes rank i. */
+int neompc_comm_init_all(neompc_handle** handles, int n_handles);
+int neompc_comm_destroy(neompc_handle* h);                 /* also done by neompc_destroy */
+int neompc_comm_info(const neompc_handle* h, int* n_ranks, int* rank);
+size_t neompc_shard_rows(size_t n_total, int n_ranks);
+/* Device buffers, asynchronous: solves this rank's shard (n_local <= shard_rows requests) on `stream`, writing its twists
+ * into rows [rank * shard_rows, ...) of d_twist_all ([n_ranks * shard_rows][3] floats, rows past a short shard zeroed),
+ * then all-gathers d_twist_all in place on the handle's communication stream behind the solve — so the caller may already
+ * enqueue the next batch's solve on `stream` (with another d_twist_all) while the gather runs.  neompc_gather_wait makes
+ * `stream` wait for the most recent gather (age 0) or for the one before it (age 1: the software-pipelined loop
+ * "solve k; wait for gather k-1"). */
+int neompc_solve_gather_device(neompc_handle* h, const neompc_request* d_reqs, size_t n_local, size_t shard_rows,
+                               neompc_response* d_out, float* d_twist_all, void* stream);
+int neompc_gather_wait(neompc_handle* h, void* stream, int age);
+/* Host buffers, synchronous, for communicators made with neompc_comm_init_all: shards `reqs`, copies each shard to its
+ * GPU, solves, all-gathers, and returns all n twists ([n][3] floats) from rank 0's copy; out_or_null receives the n
+ * responses.  neompc_fleet_get_gathered reads another rank's copy of the last gather (they are identical: test hook). */
+int neompc_fleet_solve(neompc_handle** handles, int n_handles, const neompc_request* reqs, size_t n, float* twist_out,
+                       neompc_response* out_or_null);
+int neompc_fleet_get_gathered(neompc_handle* h, size_t n, float* twist_out);
 
 /* ---- the step before the solve: carrot selection of the plugin ------------------- */
 /* One robot's inputs for one control tick: what computeVelocityCommands receives (cpp:202-205) plus the plugin state

@@ -18,6 +18,9 @@ EXPORTS = [
     "neompc_set_plan", "neompc_build_requests", "neompc_build_requests_device",
     "neompc_local_plan", "neompc_local_plan_device",
     "neompc_eval_objective", "neompc_launch_count", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
+    "neompc_comm_unique_id", "neompc_comm_init", "neompc_comm_init_all", "neompc_comm_destroy", "neompc_comm_info",
+    "neompc_shard_rows", "neompc_solve_gather_device", "neompc_gather_wait", "neompc_fleet_solve",
+    "neompc_fleet_get_gathered",
 ]
 
 _lib = None
@@ -79,5 +82,16 @@ def load():
     lib.neompc_get_tiling.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.neompc_host_alloc.argtypes = [ctypes.POINTER(vp), sz]
     lib.neompc_host_free.argtypes = [vp]
+    lib.neompc_comm_unique_id.argtypes = [vp]
+    lib.neompc_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.neompc_comm_init_all.argtypes = [ctypes.POINTER(vp), i32]
+    lib.neompc_comm_destroy.argtypes = [vp]
+    lib.neompc_comm_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    lib.neompc_shard_rows.argtypes = [sz, i32]
+    lib.neompc_shard_rows.restype = sz
+    lib.neompc_solve_gather_device.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    lib.neompc_gather_wait.argtypes = [vp, vp, i32]
+    lib.neompc_fleet_solve.argtypes = [ctypes.POINTER(vp), i32, vp, sz, vp, vp]
+    lib.neompc_fleet_get_gathered.argtypes = [vp, sz, vp]
     _lib = lib
     return lib

@@ -2,6 +2,8 @@
 // Replaces the ROS service hop between NeoMpcPlanner::computeVelocityCommands (reference src/NeoMpcPlanner.cpp:240-252)
 // and MpcOptimizationServer.optimizer (reference neo_mpc_planner2/mpc_optimization_server.py:349-403).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>       // types and prototypes only: the library is bound at run time (load_nccl), never linked
 
 #include <algorithm>
 #include <cmath>
@@ -45,6 +47,15 @@ struct neompc_handle {
   neompc_optimizer_request* d_msgs = nullptr;
   size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
   uint64_t launches = 0;
+  // multi-GPU: one NCCL communicator over the handles of a fleet; the single collective of the path is the
+  // all-gather of the solved (vx, vy, omega), enqueued on its own stream behind the solve kernel
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_solved = nullptr, ev_gathered[2] = {nullptr, nullptr};   // the two most recent gathers, alternating
+  unsigned gathers = 0;
+  float* d_gather = nullptr;        // staging of the single-process fleet entry: [n_ranks * shard_rows][3]
+  size_t cap_gather = 0;
   unsigned* err_word = nullptr;     // mapped pinned word the kernels set when a request names a missing state row
   bool debug_ids = false;           // NEOMPC_DEBUG_IDS=1: host-side uniqueness check of instance ids (slow)
   // carrot selection (row N2): shared global plan, byte -> raw-cost table, staging
@@ -292,6 +303,99 @@ int check_unique_ids(neompc_handle* h, const Rec* recs, size_t n) {
   return NEOMPC_OK;
 }
 
+
+// ---- NCCL, bound at run time --------------------------------------------------------------------------------------
+// libneompc.so carries no link-time dependency on NCCL: a controller plugin that drives one GPU never needs it, and a
+// Python host has usually loaded its own copy already (torch bundles one under the same SONAME, which dlopen then returns).
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+
+const NcclApi* load_nccl(std::string& err) {
+  static NcclApi api;
+  static bool tried = false;
+  static std::string load_err;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) {
+      load_err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "");
+    } else {
+#define NEOMPC_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+      NEOMPC_SYM(GetUniqueId, "ncclGetUniqueId");
+      NEOMPC_SYM(CommInitRank, "ncclCommInitRank");
+      NEOMPC_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
+      NEOMPC_SYM(CommDestroy, "ncclCommDestroy");
+      NEOMPC_SYM(AllGather, "ncclAllGather");
+      NEOMPC_SYM(GroupStart, "ncclGroupStart");
+      NEOMPC_SYM(GroupEnd, "ncclGroupEnd");
+      NEOMPC_SYM(GetErrorString, "ncclGetErrorString");
+      NEOMPC_SYM(GetVersion, "ncclGetVersion");
+#undef NEOMPC_SYM
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GroupStart || !api.GroupEnd)
+        load_err = "libnccl.so.2 lacks a required symbol";
+    }
+  }
+  if (!load_err.empty()) { err = load_err; return nullptr; }
+  return &api;
+}
+
+int nccl_fail(neompc_handle* h, const NcclApi* api, ncclResult_t r, const char* what) {
+  return fail(h, NEOMPC_ERR_NCCL, std::string(what) + ": " + (api && api->GetErrorString ? api->GetErrorString(r) : "NCCL error"));
+}
+
+void comm_release(neompc_handle* h) {
+  std::string err;
+  if (h->comm) {
+    const NcclApi* api = load_nccl(err);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    if (api) api->CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
+  if (h->ev_solved) { cudaEventDestroy(h->ev_solved); h->ev_solved = nullptr; }
+  for (int k = 0; k < 2; ++k)
+    if (h->ev_gathered[k]) { cudaEventDestroy(h->ev_gathered[k]); h->ev_gathered[k] = nullptr; }
+  h->gathers = 0;
+  h->n_ranks = 1; h->rank = 0;
+}
+
+// stream + events of the gather; the communicator itself is created by the callers below
+int comm_prepare(neompc_handle* h, int n_ranks, int rank) {
+  comm_release(h);
+  NEOMPC_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  NEOMPC_CUDA(h, cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) NEOMPC_CUDA(h, cudaEventCreateWithFlags(&h->ev_gathered[k], cudaEventDisableTiming));
+  h->n_ranks = n_ranks; h->rank = rank;
+  return NEOMPC_OK;
+}
+
+// The gather moves 12 B per solve (786 KB per rank at C3) while the next batch is being solved on the same SMs: NCCL is
+// held to a few CTAs so that it does not take SMs from the solve kernel (NEOMPC_NCCL_MAX_CTAS, default 2).
+ncclResult_t comm_init_rank(const NcclApi* api, ncclComm_t* comm, int n_ranks, const ncclUniqueId& id, int rank) {
+  if (api->CommInitRankConfig) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    const char* e = std::getenv("NEOMPC_NCCL_MAX_CTAS");
+    const int ctas = e ? std::atoi(e) : 2;
+    if (ctas > 0) { cfg.minCTAs = 1; cfg.maxCTAs = ctas; }
+    return api->CommInitRankConfig(comm, n_ranks, id, rank, &cfg);
+  }
+  return api->CommInitRank(comm, n_ranks, id, rank);
+}
+
 int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, neompc_response* d_out,
                     float* d_twist, float* d_plan, cudaStream_t s, size_t tiling_n = 0) {
   if (n == 0) return NEOMPC_OK;
@@ -390,6 +494,8 @@ int neompc_destroy(neompc_handle* h) {
   DeviceGuard guard__(h->device >= 0 ? h->device : 0);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  comm_release(h);
+  cudaFree(h->d_gather);
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_cells4); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
@@ -792,6 +898,213 @@ int neompc_build_requests(neompc_handle* h, const neompc_carrot_params* cp, cons
   NEOMPC_CUDA(h, cudaMemcpyAsync(reqs_out, h->d_reqs, n * sizeof(neompc_request), cudaMemcpyDeviceToHost, h->stream));
   NEOMPC_CUDA(h, cudaMemcpyAsync(info_out, h->d_info, n * sizeof(neompc_carrot_info), cudaMemcpyDeviceToHost, h->stream));
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NEOMPC_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------
+int neompc_comm_unique_id(unsigned char id[NEOMPC_COMM_ID_BYTES]) {
+  if (!id) return NEOMPC_ERR_INVALID;
+  std::string err;
+  const NcclApi* api = load_nccl(err);
+  if (!api) return fail(nullptr, NEOMPC_ERR_NCCL, err);
+  static_assert(sizeof(ncclUniqueId) == NEOMPC_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId uid;
+  ncclResult_t r = api->GetUniqueId(&uid);
+  if (r != ncclSuccess) return nccl_fail(nullptr, api, r, "ncclGetUniqueId");
+  std::memcpy(id, &uid, sizeof(uid));
+  return NEOMPC_OK;
+}
+
+int neompc_comm_init(neompc_handle* h, const unsigned char id[NEOMPC_COMM_ID_BYTES], int n_ranks, int rank) {
+  if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, NEOMPC_ERR_INVALID, "bad communicator arguments");
+  std::string err;
+  const NcclApi* api = load_nccl(err);
+  if (!api) return fail(h, NEOMPC_ERR_NCCL, err);
+  NEOMPC_DEVICE(h);
+  int rc = comm_prepare(h, n_ranks, rank);
+  if (rc != NEOMPC_OK) return rc;
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclResult_t r = comm_init_rank(api, &h->comm, n_ranks, uid, rank);
+  if (r != ncclSuccess) { comm_release(h); return nccl_fail(h, api, r, "ncclCommInitRank"); }
+  return NEOMPC_OK;
+}
+
+int neompc_comm_init_all(neompc_handle** handles, int n_handles) {
+  if (!handles || n_handles < 1) return NEOMPC_ERR_INVALID;
+  for (int i = 0; i < n_handles; ++i) {
+    if (!handles[i]) return NEOMPC_ERR_INVALID;
+    for (int j = 0; j < i; ++j)
+      if (handles[j]->device == handles[i]->device) return fail(handles[0], NEOMPC_ERR_INVALID, "two handles of a fleet share a device");
+  }
+  neompc_handle* h0 = handles[0];
+  std::string err;
+  const NcclApi* api = load_nccl(err);
+  if (!api) return fail(h0, NEOMPC_ERR_NCCL, err);
+  ncclUniqueId uid;
+  ncclResult_t r = api->GetUniqueId(&uid);
+  if (r != ncclSuccess) return nccl_fail(h0, api, r, "ncclGetUniqueId");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  int rc = NEOMPC_OK;
+  for (int i = 0; i < n_handles && rc == NEOMPC_OK; ++i) {
+    cudaSetDevice(handles[i]->device);
+    rc = comm_prepare(handles[i], n_handles, i);
+  }
+  if (rc == NEOMPC_OK) {
+    // one process, several devices: the ranks are initialised inside one NCCL group (what ncclCommInitAll does)
+    r = api->GroupStart();
+    for (int i = 0; i < n_handles && r == ncclSuccess; ++i) {
+      cudaSetDevice(handles[i]->device);
+      r = comm_init_rank(api, &handles[i]->comm, n_handles, uid, i);
+    }
+    ncclResult_t re = api->GroupEnd();
+    if (r == ncclSuccess) r = re;
+    if (r != ncclSuccess) {
+      for (int i = 0; i < n_handles; ++i) { cudaSetDevice(handles[i]->device); comm_release(handles[i]); }
+      rc = nccl_fail(h0, api, r, "ncclCommInitRank (group)");
+    }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int neompc_comm_destroy(neompc_handle* h) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  NEOMPC_DEVICE(h);
+  comm_release(h);
+  return NEOMPC_OK;
+}
+
+int neompc_comm_info(const neompc_handle* h, int* n_ranks, int* rank) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  if (n_ranks) *n_ranks = h->n_ranks;
+  if (rank) *rank = h->rank;
+  return NEOMPC_OK;
+}
+
+size_t neompc_shard_rows(size_t n_total, int n_ranks) {
+  return n_ranks > 0 ? (n_total + (size_t)n_ranks - 1) / (size_t)n_ranks : 0;
+}
+
+// enqueue only (no group call, no synchronise): solve of the local shard into its slot + event + all-gather
+static int solve_gather_enqueue(neompc_handle* h, const NcclApi* api, const neompc_request* d_reqs, size_t n_local,
+                                size_t shard_rows, neompc_response* d_out, float* d_twist_all, cudaStream_t s, bool gather) {
+  if (n_local > shard_rows) return fail(h, NEOMPC_ERR_INVALID, "local shard larger than shard_rows");
+  float* slot = d_twist_all + (size_t)h->rank * shard_rows * 3;
+  if (n_local < shard_rows)      // rows of the slot past the shard travel with the collective: defined contents
+    NEOMPC_CUDA(h, cudaMemsetAsync(slot + n_local * 3, 0, (shard_rows - n_local) * 3 * sizeof(float), s));
+  int rc = do_solve_device(h, d_reqs, n_local, d_out, slot, nullptr, s);
+  if (rc != NEOMPC_OK) return rc;
+  if (h->n_ranks > 1 || h->comm) {
+    NEOMPC_CUDA(h, cudaEventRecord(h->ev_solved, s));
+    NEOMPC_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_solved, 0));
+    if (gather) {
+      ncclResult_t r = api->AllGather(slot, d_twist_all, shard_rows * 3, ncclFloat, h->comm, h->comm_stream);
+      if (r != ncclSuccess) return nccl_fail(h, api, r, "ncclAllGather");
+      NEOMPC_CUDA(h, cudaEventRecord(h->ev_gathered[h->gathers & 1u], h->comm_stream));
+      h->gathers += 1;
+    }
+  }
+  return NEOMPC_OK;
+}
+
+int neompc_solve_gather_device(neompc_handle* h, const neompc_request* d_reqs, size_t n_local, size_t shard_rows,
+                               neompc_response* d_out, float* d_twist_all, void* stream) {
+  if (!h || !d_twist_all || (n_local > 0 && (!d_reqs || !d_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (!h->comm) return fail(h, NEOMPC_ERR_INVALID, "no communicator (neompc_comm_init / neompc_comm_init_all)");
+  std::string err;
+  const NcclApi* api = load_nccl(err);
+  if (!api) return fail(h, NEOMPC_ERR_NCCL, err);
+  NEOMPC_DEVICE(h);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  return solve_gather_enqueue(h, api, d_reqs, n_local, shard_rows, d_out, d_twist_all, s, true);
+}
+
+int neompc_gather_wait(neompc_handle* h, void* stream, int age) {
+  if (!h || age < 0 || age > 1) return NEOMPC_ERR_INVALID;
+  if (!h->comm || h->gathers <= (unsigned)age) return NEOMPC_OK;          // no such gather yet
+  NEOMPC_DEVICE(h);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  NEOMPC_CUDA(h, cudaStreamWaitEvent(s, h->ev_gathered[(h->gathers - 1u - (unsigned)age) & 1u], 0));
+  return NEOMPC_OK;
+}
+
+int neompc_fleet_solve(neompc_handle** handles, int n_handles, const neompc_request* reqs, size_t n, float* twist_out,
+                       neompc_response* out_or_null) {
+  if (!handles || n_handles < 1 || (n > 0 && (!reqs || !twist_out))) return NEOMPC_ERR_INVALID;
+  neompc_handle* h0 = handles[0];
+  for (int i = 0; i < n_handles; ++i)
+    if (!handles[i] || !handles[i]->comm || handles[i]->n_ranks != n_handles || handles[i]->rank != i)
+      return fail(h0, NEOMPC_ERR_INVALID, "handles are not the ranks 0..n-1 of one communicator (neompc_comm_init_all)");
+  if (n == 0) return NEOMPC_OK;
+  std::string err;
+  const NcclApi* api = load_nccl(err);
+  if (!api) return fail(h0, NEOMPC_ERR_NCCL, err);
+  const size_t rows = neompc_shard_rows(n, n_handles);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  int rc = NEOMPC_OK;
+  // 1. per device: staging, H2D of the shard, solve into the shard's slot of that device's gather buffer
+  for (int i = 0; i < n_handles && rc == NEOMPC_OK; ++i) {
+    neompc_handle* h = handles[i];
+    cudaSetDevice(h->device);
+    const size_t lo = std::min(n, (size_t)i * rows), hi = std::min(n, (size_t)(i + 1) * rows), cnt = hi - lo;
+    rc = check_unique_ids(h, reqs + lo, cnt);
+    if (rc == NEOMPC_OK) rc = ensure_staging(h, rows, false, false);
+    if (rc == NEOMPC_OK && (size_t)n_handles * rows * 3 > h->cap_gather) {
+      cudaFree(h->d_gather);
+      h->d_gather = nullptr; h->cap_gather = 0;
+      cudaError_t e = cudaMalloc(&h->d_gather, (size_t)n_handles * rows * 3 * sizeof(float));
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "cudaMalloc(gather)"); else h->cap_gather = (size_t)n_handles * rows * 3;
+    }
+    if (rc != NEOMPC_OK) break;
+    if (cnt > 0) {
+      cudaError_t e = cudaMemcpyAsync(h->d_reqs, reqs + lo, cnt * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream);
+      if (e != cudaSuccess) { rc = cuda_fail(h, e, "H2D requests"); break; }
+    }
+    rc = solve_gather_enqueue(h, api, h->d_reqs, cnt, rows, h->d_resp, h->d_gather, h->stream, false);
+    if (rc == NEOMPC_OK && out_or_null && cnt > 0) {
+      cudaError_t e = cudaMemcpyAsync(out_or_null + lo, h->d_resp, cnt * sizeof(neompc_response), cudaMemcpyDeviceToHost, h->stream);
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H responses");
+    }
+  }
+  // 2. the single collective of the path, all ranks of this process in one NCCL group
+  if (rc == NEOMPC_OK) {
+    ncclResult_t r = api->GroupStart();
+    for (int i = 0; i < n_handles && r == ncclSuccess; ++i) {
+      neompc_handle* h = handles[i];
+      cudaSetDevice(h->device);
+      r = api->AllGather(h->d_gather + (size_t)i * rows * 3, h->d_gather, rows * 3, ncclFloat, h->comm, h->comm_stream);
+    }
+    ncclResult_t re = api->GroupEnd();
+    if (r == ncclSuccess) r = re;
+    if (r != ncclSuccess) rc = nccl_fail(h0, api, r, "ncclAllGather (group)");
+  }
+  // 3. every device now holds all twists; rank 0's copy goes to the host
+  if (rc == NEOMPC_OK) {
+    cudaSetDevice(h0->device);
+    cudaError_t e = cudaMemcpyAsync(twist_out, h0->d_gather, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h0->comm_stream);
+    if (e != cudaSuccess) rc = cuda_fail(h0, e, "D2H twists");
+  }
+  for (int i = 0; i < n_handles; ++i) {
+    neompc_handle* h = handles[i];
+    cudaSetDevice(h->device);
+    cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->comm_stream);
+    if (rc == NEOMPC_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = cuda_fail(h, e1 != cudaSuccess ? e1 : e2, "fleet synchronise");
+    if (rc == NEOMPC_OK) rc = check_state_errors(h);
+    if (rc != NEOMPC_OK && h != h0) h0->err = h->err;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int neompc_fleet_get_gathered(neompc_handle* h, size_t n, float* twist_out) {
+  if (!h || !twist_out) return NEOMPC_ERR_INVALID;
+  if (n * 3 > h->cap_gather) return fail(h, NEOMPC_ERR_INVALID, "no gathered batch of that size on this handle");
+  NEOMPC_DEVICE(h);
+  NEOMPC_CUDA(h, cudaMemcpyAsync(twist_out, h->d_gather, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->comm_stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->comm_stream));
   return NEOMPC_OK;
 }
 

@@ -148,6 +148,40 @@ class BatchSolver:
             ctypes.c_void_p(d_twist) if d_twist else None, ctypes.c_void_p(d_plan) if d_plan else None,
             ctypes.c_void_p(stream) if stream else None), "neompc_solve_batch_device")
 
+    # ------------------------------------------------------------------ multi-GPU: one rank of a fleet (include/neompc.h)
+    @staticmethod
+    def comm_unique_id():
+        """128 opaque bytes rank 0 creates and the caller distributes (neompc_comm_unique_id)."""
+        lib = _lib.load()
+        buf = (ctypes.c_ubyte * 128)()
+        rc = lib.neompc_comm_unique_id(buf)
+        if rc != 0:
+            raise NeompcError(f"neompc_comm_unique_id failed ({rc}): {lib.neompc_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.neompc_comm_init(self._h, buf, int(n_ranks), int(rank)), "neompc_comm_init")
+
+    def comm_info(self):
+        n, r = ctypes.c_int(), ctypes.c_int()
+        self._lib.neompc_comm_info(self._h, ctypes.byref(n), ctypes.byref(r))
+        return n.value, r.value
+
+    def solve_gather_device(self, d_reqs, n_local, shard_rows, d_out, d_twist_all, stream=None):
+        """This rank's shard + the all-gather of every rank's (vx, vy, omega) into d_twist_all [n_ranks*shard_rows, 3]."""
+        if stream == 0:
+            stream = 1
+        self._check(self._lib.neompc_solve_gather_device(
+            self._h, ctypes.c_void_p(d_reqs), int(n_local), int(shard_rows), ctypes.c_void_p(d_out),
+            ctypes.c_void_p(d_twist_all), ctypes.c_void_p(stream) if stream else None), "neompc_solve_gather_device")
+
+    def gather_wait(self, stream=None, age=0):
+        if stream == 0:
+            stream = 1
+        self._check(self._lib.neompc_gather_wait(self._h, ctypes.c_void_p(stream) if stream else None, int(age)),
+                    "neompc_gather_wait")
+
     def solve_msgs(self, msgs, want_plan=False):
         msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
         n = len(msgs)

@@ -58,10 +58,19 @@ def test_gather_is_shard_invariant(world, n_total):
 
 
 def test_shard_bounds_cover_everything():
+    """Contiguous cover, every shard at most ceil(n / world) rows — the library's neompc_shard_rows — so that the gathered
+    rows of all ranks are contiguous; only trailing shards may be short or empty."""
+    import ctypes
+    from neo_mpc_planner2_b200 import _lib
+    lib = _lib.load()
     for n in (0, 1, 7, 4096, 65537, 1048576):
         for world in (1, 2, 3, 4, 8):
+            m = max_shard(n, world)
+            assert m == lib.neompc_shard_rows(ctypes.c_size_t(n), world)
             edges = [shard_bounds(n, world, r) for r in range(world)]
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
-            assert max(sizes) - min(sizes) <= 1 and max(sizes) == max_shard(n, world)
+            assert max(sizes) <= m and all(a == r * m or a == n for r, (a, b) in enumerate(edges))
+            full = [sz for sz in sizes if sz == m]
+            assert sizes[:len(full)] == full            # full shards first, then at most one short one, then empty ones
