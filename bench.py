@@ -424,6 +424,22 @@ def run_ours(args):
         lat = {"n": 1, "api": "neompc_solve_msgs (pack + solve + D2H, cold start)", "median_us": 1e6 * float(np.median(ts)),
                "p99_us": 1e6 * float(np.percentile(ts, 99))}
 
+    # ---- full controller tick through the C++ plugin (NeoMpcPlanner::computeVelocityCommands over libneompc: costmap
+    # checksum / upload when it changed, front half, solve, one synchronise), control_steps = 10, on a 60x60 local
+    # costmap and on a 1000x1000 one
+    plugin_lat = None
+    demo = os.path.join(ROOT, "neo_mpc_planner2_b200", "plugin", "plugin_demo")
+    if rank == 0 and os.path.exists(demo):
+        import subprocess
+        plugin_lat = []
+        for w, h in ((60, 60), (1000, 1000)):
+            try:
+                r = subprocess.run([demo, "latency", str(w), str(h)], capture_output=True, text=True, timeout=120,
+                                   env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local))))
+                plugin_lat.append(json.loads(r.stdout.strip().splitlines()[-1]))
+            except Exception as exc:
+                plugin_lat.append({"costmap": [w, h], "error": str(exc)})
+
     resp = np.frombuffer(resp_host.numpy().tobytes(), dtype=RESPONSE_DTYPE)
     iters_med = float(np.median(resp["iters"]))
     evals_mean = float(resp["evals"].mean())
@@ -478,6 +494,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "single_request_latency": lat,
+            "plugin_tick_latency": plugin_lat,
             "sustained": sustained,
         }
         if world == 1 and not args.no_cpu_baseline and not args.footprint_mode and not args.costmap_mode:

@@ -302,6 +302,14 @@ int neompc_build_requests_device(neompc_handle* h, const neompc_carrot_params* c
                                  size_t n, uint32_t first_instance_id, neompc_request* d_reqs_out,
                                  neompc_carrot_info* d_info_out, void* stream);
 
+/* One control tick for n robots in one call — carrot selection + request construction feeding the solve on the device,
+ * one synchronise: what NeoMpcPlanner::computeVelocityCommands (cpp:202-255) does per call, without the service hop.
+ * Every robot is solved, also those whose info.status is not NEOMPC_CARROT_OK (the caller decides what to do with them: the
+ * reference throws ControllerException, cpp:131, :235).  reqs_out_or_null receives the requests that were solved. */
+int neompc_control_tick(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* ticks, size_t n,
+                        uint32_t first_instance_id, neompc_response* out, neompc_carrot_info* info_out,
+                        neompc_request* reqs_out_or_null, float* plan_or_null);
+
 /* ---- the step after the solve: the predicted path -------------------------------- */
 /* One pose of the nav_msgs/Path the reference publishes on "local_plan" (srv.py:107; publishLocalPlan, srv.py:271-310):
  * position x, y and the orientation quaternion_from_euler(0, 0, yaw) (srv.py:182-196; x = y = 0).  32 bytes. */

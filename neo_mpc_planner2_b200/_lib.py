@@ -20,7 +20,7 @@ EXPORTS = [
     "neompc_eval_objective", "neompc_launch_count", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
     "neompc_comm_unique_id", "neompc_comm_init", "neompc_comm_init_all", "neompc_comm_destroy", "neompc_comm_info",
     "neompc_shard_rows", "neompc_solve_gather_device", "neompc_gather_wait", "neompc_fleet_solve",
-    "neompc_fleet_get_gathered",
+    "neompc_fleet_get_gathered", "neompc_control_tick",
 ]
 
 _lib = None
@@ -41,6 +41,17 @@ def build(verbose=False):
     if res.returncode != 0:
         raise NeompcError("building libneompc.so failed")
     return LIB_PATH
+
+
+def prefer_torch_nccl():
+    """libneompc binds NCCL at run time and takes the copy the process has loaded already.  In a Python process that copy
+    should be torch's (bundled, same SONAME as the system's): binding the system copy first would break a later
+    `import torch`.  Called before the first communicator call."""
+    try:
+        import torch  # noqa: F401
+        import torch.distributed  # noqa: F401
+    except Exception:  # no torch: the system's libnccl.so.2 is used
+        pass
 
 
 def load():
@@ -93,5 +104,6 @@ def load():
     lib.neompc_gather_wait.argtypes = [vp, vp, i32]
     lib.neompc_fleet_solve.argtypes = [ctypes.POINTER(vp), i32, vp, sz, vp, vp]
     lib.neompc_fleet_get_gathered.argtypes = [vp, sz, vp]
+    lib.neompc_control_tick.argtypes = [vp, vp, vp, sz, u32, vp, vp, vp, vp]
     _lib = lib
     return lib

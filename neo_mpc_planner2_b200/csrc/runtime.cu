@@ -73,6 +73,8 @@ struct neompc_handle {
   neompc_request* mb_reqs = nullptr;
   neompc_response* mb_resp = nullptr;
   float* mb_plan = nullptr;
+  neompc_robot_tick* mb_ticks = nullptr;
+  neompc_carrot_info* mb_info = nullptr;
   std::string err;
 };
 
@@ -326,10 +328,15 @@ const NcclApi* load_nccl(std::string& err) {
   static std::string load_err;
   if (!tried) {
     tried = true;
+    // 1. a copy this process has loaded already (a Python host's torch bundles one under the same SONAME: binding to
+    //    another copy first would break a later `import torch`; the Python binding imports torch first for that reason);
+    // 2. NEOMPC_NCCL_LIB, an explicit path;  3. the system's libnccl.so.2.
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!api.lib && std::getenv("NEOMPC_NCCL_LIB")) api.lib = dlopen(std::getenv("NEOMPC_NCCL_LIB"), RTLD_NOW | RTLD_LOCAL);
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (api.lib) break;
+      api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     }
     if (!api.lib) {
       load_err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "");
@@ -480,6 +487,8 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   CREATE_CUDA(cudaHostAlloc(&h->mb_reqs, kMailboxRequests * sizeof(neompc_request), cudaHostAllocMapped));
   CREATE_CUDA(cudaHostAlloc(&h->mb_resp, kMailboxRequests * sizeof(neompc_response), cudaHostAllocMapped));
   CREATE_CUDA(cudaHostAlloc(&h->mb_plan, kMailboxRequests * 3 * NEOMPC_MAX_CONTROL_STEPS * sizeof(float), cudaHostAllocMapped));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_ticks, kMailboxRequests * sizeof(neompc_robot_tick), cudaHostAllocMapped));
+  CREATE_CUDA(cudaHostAlloc(&h->mb_info, kMailboxRequests * sizeof(neompc_carrot_info), cudaHostAllocMapped));
 #undef CREATE_CUDA
   build_const(h->params, h->c);
   rebuild_const(h);
@@ -499,7 +508,7 @@ int neompc_destroy(neompc_handle* h) {
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_cells4); cudaFree(h->d_state);
   cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
-  cudaFreeHost(h->err_word); cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan);
+  cudaFreeHost(h->err_word); cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan); cudaFreeHost(h->mb_ticks); cudaFreeHost(h->mb_info);
   delete h;
   return NEOMPC_OK;
 }
@@ -1106,6 +1115,57 @@ int neompc_fleet_get_gathered(neompc_handle* h, size_t n, float* twist_out) {
   NEOMPC_CUDA(h, cudaMemcpyAsync(twist_out, h->d_gather, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->comm_stream));
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->comm_stream));
   return NEOMPC_OK;
+}
+
+// One control tick for n robots, fused: carrot selection + request construction (cpp:66-246) feeding the solve
+// (srv.py:349-403) on the device, one synchronise.  What NeoMpcPlanner::computeVelocityCommands does per call.
+int neompc_control_tick(neompc_handle* h, const neompc_carrot_params* cp, const neompc_robot_tick* ticks, size_t n,
+                        uint32_t first_instance_id, neompc_response* out, neompc_carrot_info* info_out,
+                        neompc_request* reqs_out_or_null, float* plan_or_null) {
+  if (!h || !cp || (n > 0 && (!ticks || !out || !info_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_DEVICE(h);
+  int rc = ensure_staging(h, n, plan_or_null != nullptr, false);
+  if (rc != NEOMPC_OK) return rc;
+  const size_t n3 = n * 3 * (size_t)h->params.control_steps;
+  const bool small = n <= kMailboxRequests;
+  if (!small && n > h->cap_ticks) {
+    if (h->d_ticks) cudaFree(h->d_ticks);
+    if (h->d_info) cudaFree(h->d_info);
+    h->d_ticks = nullptr; h->d_info = nullptr; h->cap_ticks = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_ticks, n * sizeof(neompc_robot_tick)));
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_info, n * sizeof(neompc_carrot_info)));
+    h->cap_ticks = n;
+  }
+  const neompc_robot_tick* d_ticks = h->d_ticks;
+  neompc_carrot_info* d_info = h->d_info;
+  neompc_response* d_resp = h->d_resp;
+  float* d_plan = plan_or_null ? h->d_plan : nullptr;
+  if (small) {                                   // controller tick: mapped mailboxes, no staged copies
+    std::memcpy(h->mb_ticks, ticks, n * sizeof(neompc_robot_tick));
+    d_ticks = h->mb_ticks; d_info = h->mb_info; d_resp = h->mb_resp;
+    d_plan = plan_or_null ? h->mb_plan : nullptr;
+  } else {
+    NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_ticks, ticks, n * sizeof(neompc_robot_tick), cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = neompc_build_requests_device(h, cp, d_ticks, n, first_instance_id, h->d_reqs, d_info, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  rc = do_solve_device(h, h->d_reqs, n, d_resp, nullptr, d_plan, h->stream);
+  if (rc != NEOMPC_OK) return rc;
+  if (!small) {
+    NEOMPC_CUDA(h, cudaMemcpyAsync(out, h->d_resp, n * sizeof(neompc_response), cudaMemcpyDeviceToHost, h->stream));
+    NEOMPC_CUDA(h, cudaMemcpyAsync(info_out, h->d_info, n * sizeof(neompc_carrot_info), cudaMemcpyDeviceToHost, h->stream));
+    if (plan_or_null) NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null, h->d_plan, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (reqs_out_or_null)
+    NEOMPC_CUDA(h, cudaMemcpyAsync(reqs_out_or_null, h->d_reqs, n * sizeof(neompc_request), cudaMemcpyDeviceToHost, h->stream));
+  NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (small) {
+    std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
+    std::memcpy(info_out, h->mb_info, n * sizeof(neompc_carrot_info));
+    if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3 * sizeof(float));
+  }
+  return check_state_errors(h);
 }
 
 uint64_t neompc_launch_count(const neompc_handle* h) { return h ? h->launches : 0; }

@@ -111,6 +111,7 @@ class LocalFleet:
         from . import _lib
         from .solver import BatchSolver
         self._lib = _lib.load()
+        _lib.prefer_torch_nccl()
         self.solvers = [BatchSolver(params, device=d, **over) for d in devices]
         self._arr = (ctypes.c_void_p * len(self.solvers))(*[s._h for s in self.solvers])
         rc = self._lib.neompc_comm_init_all(self._arr, len(self.solvers))

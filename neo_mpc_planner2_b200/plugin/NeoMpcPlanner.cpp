@@ -1,10 +1,16 @@
-// NeoMpcPlanner.cpp — controller plugin body with the optimizer service call (reference src/NeoMpcPlanner.cpp:240-252)
-// replaced by an in-process libneompc call.  See INTEGRATION.md.  The plan-following front half of the reference
-// (TF transforms, pruning, slow-down hysteresis; cpp:66-232) is row N2 of SURVEY.md §8f and is reduced here to the
-// carrot pick computeVelocityCommands needs, for plans already expressed in the costmap's global frame.
+// NeoMpcPlanner.cpp — the reference's controller plugin (src/NeoMpcPlanner.cpp) with the ROS service hop to the Python
+// optimisation server (cpp:240-252) replaced by in-process libneompc calls.  One control tick is ONE library call,
+// neompc_control_tick: the plan-following front half — closest plan pose, pruning, costmap window, lookahead distance under
+// slow_down_, lookahead point, slow-down hysteresis, the footprint_cost == 255 test (cpp:66-135, 157-189, 216-236) — and the
+// request construction (cpp:240-246) run on the device and feed the solve (srv.py:349-403) without leaving it.  The plugin
+// keeps what the reference keeps per instance (pruned plan position cpp:127, slow_down_ h:162, goal_pose cpp:280) and throws
+// the reference's ControllerExceptions (cpp:70, :76, :131, :235).  See INTEGRATION.md.
+// TF: the library works in ONE frame.  A plan whose frame_id differs from the frame of the controller's pose is refused
+// with the reference's "Unable to transform ..." exception (cpp:76) instead of being followed in the wrong frame.
 #include "NeoMpcPlanner.h"
 
 #include <cmath>
+#include <cstring>
 #include <limits>
 
 #include "pluginlib/class_list_macros.hpp"
@@ -14,10 +20,6 @@ namespace neo_mpc_planner {
 namespace {
 double yawOf(const geometry_msgs::msg::Quaternion & q) {
   return std::atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));
-}
-void putPose(double * dst, const geometry_msgs::msg::Pose & p) {
-  dst[0] = p.position.x; dst[1] = p.position.y; dst[2] = p.position.z;
-  dst[3] = p.orientation.x; dst[4] = p.orientation.y; dst[5] = p.orientation.z; dst[6] = p.orientation.w;
 }
 }  // namespace
 
@@ -79,100 +81,118 @@ void NeoMpcPlanner::activate() {}
 void NeoMpcPlanner::deactivate() {}
 
 void NeoMpcPlanner::setPlan(const nav_msgs::msg::Path & plan) {                      // reference cpp:274-281
+  std::lock_guard<std::mutex> lock(mutex_);
   global_plan_ = plan;
-  if (!plan.poses.empty()) goal_pose_ = plan.poses.back().pose;
+  plan_start_ = 0;                                    // a new plan is un-pruned (the reference erases from its own copy, cpp:127)
+  if (plan.poses.empty()) return;
+  if (goal_pose_ != plan.poses.back().pose) slow_down_ = true;                       // cpp:277-279
+  goal_pose_ = plan.poses.back().pose;
+  if (!mpc_) return;
+  std::vector<double> xyyaw;
+  xyyaw.reserve(3 * plan.poses.size());
+  for (const auto & ps : plan.poses) {
+    xyyaw.push_back(ps.pose.position.x);
+    xyyaw.push_back(ps.pose.position.y);
+    xyyaw.push_back(yawOf(ps.pose.orientation));
+  }
+  if (neompc_set_plan(mpc_, xyyaw.data(), plan.poses.size()) != NEOMPC_OK)
+    throw nav2_core::ControllerException(std::string("neompc_set_plan failed: ") + neompc_last_error(mpc_));
 }
 
 void NeoMpcPlanner::setSpeedLimit(const double &, const bool &) {}                   // empty in the reference too (cpp:283-288)
 
-void NeoMpcPlanner::uploadCostmap() {
+// The costmap goes to the device only when it changed: geometry compare + a 64-bit checksum of the cells, taken under the
+// costmap's own mutex (controller_server updates the local costmap on another thread).  Returns true if it uploaded.
+bool NeoMpcPlanner::uploadCostmapIfChanged() {
   auto * cm = costmap_ros_->getCostmap();
-  if (neompc_set_costmap(mpc_, cm->getCharMap(), cm->getSizeInCellsX(), cm->getSizeInCellsY(), cm->getResolution(),
-                         cm->getOriginX(), cm->getOriginY(), NEOMPC_ENC_NAV2_RAW) != NEOMPC_OK)
+  std::unique_lock<nav2_costmap_2d::Costmap2D::mutex_t> lock(*cm->getMutex());
+  const unsigned w = cm->getSizeInCellsX(), h = cm->getSizeInCellsY();
+  const unsigned char * cells = cm->getCharMap();
+  const size_t bytes = (size_t)w * h;
+  uint64_t acc[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t v[4];
+    std::memcpy(v, cells + i, 32);
+    for (int k = 0; k < 4; ++k) acc[k] = (acc[k] ^ v[k]) * 0x100000001B3ull + (acc[k] >> 29);
+  }
+  for (; i < bytes; ++i) acc[i & 3] = (acc[i & 3] ^ cells[i]) * 0x100000001B3ull;
+  const uint64_t sum = acc[0] ^ (acc[1] << 1) ^ (acc[2] << 2) ^ (acc[3] << 3);
+  const bool same = costmap_loaded_ && sum == costmap_sum_ && w == costmap_w_ && h == costmap_h_ &&
+                    cm->getResolution() == costmap_res_ && cm->getOriginX() == costmap_ox_ && cm->getOriginY() == costmap_oy_;
+  if (same) return false;
+  if (neompc_set_costmap(mpc_, cells, w, h, cm->getResolution(), cm->getOriginX(), cm->getOriginY(), NEOMPC_ENC_NAV2_RAW) !=
+      NEOMPC_OK)
     throw nav2_core::ControllerException(std::string("neompc_set_costmap failed: ") + neompc_last_error(mpc_));
-}
-
-// Carrot = first plan pose, from the pose closest to the robot onwards, at least `lookahead` away; expressed in the
-// robot base frame (what the reference sends as carrot_pose, cpp:114,124,173-189).
-geometry_msgs::msg::PoseStamped NeoMpcPlanner::pickCarrot(const geometry_msgs::msg::PoseStamped & robot,
-                                                          double lookahead) {
-  const auto & poses = global_plan_.poses;
-  size_t start = 0;
-  double best = std::numeric_limits<double>::max();
-  for (size_t i = 0; i < poses.size(); ++i) {
-    const double d = std::hypot(poses[i].pose.position.x - robot.pose.position.x,
-                                poses[i].pose.position.y - robot.pose.position.y);
-    if (d < best) { best = d; start = i; }
-  }
-  size_t pick = poses.size() - 1;
-  for (size_t i = start; i < poses.size(); ++i) {
-    if (std::hypot(poses[i].pose.position.x - robot.pose.position.x,
-                   poses[i].pose.position.y - robot.pose.position.y) >= lookahead) { pick = i; break; }
-  }
-  const double yaw = yawOf(robot.pose.orientation), c = std::cos(yaw), s = std::sin(yaw);
-  const double dx = poses[pick].pose.position.x - robot.pose.position.x;
-  const double dy = poses[pick].pose.position.y - robot.pose.position.y;
-  geometry_msgs::msg::PoseStamped carrot;
-  carrot.header.frame_id = costmap_ros_->getBaseFrameID();
-  carrot.pose.position.x = c * dx + s * dy;
-  carrot.pose.position.y = -s * dx + c * dy;
-  const double rel = yawOf(poses[pick].pose.orientation) - yaw;
-  carrot.pose.orientation.z = std::sin(0.5 * rel);
-  carrot.pose.orientation.w = std::cos(0.5 * rel);
-  return carrot;
+  costmap_loaded_ = true; costmap_sum_ = sum; costmap_w_ = w; costmap_h_ = h;
+  costmap_res_ = cm->getResolution(); costmap_ox_ = cm->getOriginX(); costmap_oy_ = cm->getOriginY();
+  return true;
 }
 
 geometry_msgs::msg::TwistStamped NeoMpcPlanner::computeVelocityCommands(
     const geometry_msgs::msg::PoseStamped & position, const geometry_msgs::msg::Twist & speed,
     nav2_core::GoalChecker *) {
   std::lock_guard<std::mutex> lock(mutex_);                                           // reference cpp:207
-  if (global_plan_.poses.empty()) throw nav2_core::ControllerException("Received plan with zero length");
+  if (global_plan_.poses.empty()) throw nav2_core::ControllerException("Received plan with zero length");   // cpp:69-71
   if (!mpc_) throw nav2_core::ControllerException("controller not configured");
+  // transformPose (cpp:73-77): the robot pose must be expressible in the plan's frame.  Same frame -> nothing to do;
+  // anything else would need TF, which this port does not carry: refuse instead of following the plan in the wrong frame.
+  const std::string & plan_frame = global_plan_.header.frame_id;
+  const std::string pose_frame = position.header.frame_id.empty() ? costmap_ros_->getGlobalFrameID() : position.header.frame_id;
+  if (!plan_frame.empty() && plan_frame != pose_frame)
+    throw nav2_core::ControllerException("Unable to transform robot pose into global plan's frame");
 
-  const double to_goal = std::hypot(goal_pose_.position.x - position.pose.position.x,
-                                    goal_pose_.position.y - position.pose.position.y);
-  closer_to_goal_ = to_goal <= lookahead_dist_close_to_goal_;
-  const double lookahead = closer_to_goal_ ? lookahead_dist_close_to_goal_ : lookahead_dist_max_;
-  const auto carrot_pose = pickCarrot(position, lookahead);
+  last_upload_ = uploadCostmapIfChanged();
 
-  uploadCostmap();
-
-  // the Optimizer request (reference cpp:240-246), marshalled for the C ABI
-  neompc_optimizer_request m{};
-  m.current_vel[0] = speed.linear.x; m.current_vel[1] = speed.linear.y; m.current_vel[2] = speed.linear.z;
-  m.current_vel[3] = speed.angular.x; m.current_vel[4] = speed.angular.y; m.current_vel[5] = speed.angular.z;
-  putPose(m.carrot_pose, carrot_pose.pose);
-  putPose(m.goal_pose, goal_pose_);
-  putPose(m.current_pose, position.pose);
-  m.switch_opt = closer_to_goal_ ? 1u : 0u;
-  m.control_interval = 1.0 / control_frequency_;
+  // one tick: front half + request + solve (cpp:209-252)
+  neompc_robot_tick tick{};
+  tick.pose_x = position.pose.position.x;
+  tick.pose_y = position.pose.position.y;
+  tick.pose_yaw = yawOf(position.pose.orientation);
+  tick.vel_x = (float)speed.linear.x; tick.vel_y = (float)speed.linear.y; tick.vel_theta = (float)speed.angular.z;
+  tick.plan_start = plan_start_;
+  tick.slow_down = slow_down_ ? 1u : 0u;
   const double now = clock_ ? clock_->now().seconds() : 0.0;
-  m.delta_t = now - last_call_time_;                                                  // srv.py:369-371
+  tick.delta_t = (float)std::fmin(now - last_call_time_, 3.0e38);                     // srv.py:369-371
   last_call_time_ = now;
-  m.instance_id = 0;
+  neompc_carrot_params cp{};
+  cp.lookahead_dist_min = (float)lookahead_dist_min_;
+  cp.lookahead_dist_max = (float)lookahead_dist_max_;
+  cp.lookahead_dist_close_to_goal = (float)lookahead_dist_close_to_goal_;
+  cp.controller_frequency = (float)control_frequency_;
+  const int rc = neompc_control_tick(mpc_, &cp, &tick, 1, 0u, &last_response_, &last_info_, &last_request_, last_plan_.data());
+  if (rc != NEOMPC_OK)
+    throw nav2_core::ControllerException(std::string("neompc_control_tick failed: ") + neompc_last_error(mpc_));
+  local_plan_valid_ = false;
 
-  // the blocking service call and the response read (reference cpp:248-252)
-  if (neompc_solve_msgs(mpc_, &m, 1, &last_response_, last_plan_.data()) != NEOMPC_OK)
-    throw nav2_core::ControllerException(std::string("neompc_solve_msgs failed: ") + neompc_last_error(mpc_));
+  // the state the reference carries from tick to tick, updated before its exceptions can fire (cpp:127, :216-232)
+  plan_start_ = last_info_.plan_start;
+  closer_to_goal_ = (last_info_.flags & 1u) != 0;
+  if (last_info_.status == NEOMPC_CARROT_EMPTY_WINDOW)
+    throw nav2_core::ControllerException("Resulting plan has 0 poses in it.");        // cpp:130-132
+  slow_down_ = (last_info_.flags & 2u) != 0;
+  if (last_info_.status == NEOMPC_CARROT_COLLISION)
+    throw nav2_core::ControllerException("MPC detected collision!");                  // cpp:234-236
 
-  // the predicted path the Python server published on /mpc_local_plan (publishLocalPlan, srv.py:271-310, called :365)
-  {
-    neompc_request rq{};
-    rq.pose_x = (float)position.pose.position.x;
-    rq.pose_y = (float)position.pose.position.y;
-    const auto & q = position.pose.orientation;
-    rq.pose_yaw = (float)std::atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));   // srv.py:176-178
-    last_local_plan_.resize((size_t)params_.control_steps + 1);
-    if (neompc_local_plan(mpc_, &rq, last_plan_.data(), 1, last_local_plan_.data()) != NEOMPC_OK)
-      throw nav2_core::ControllerException(std::string("neompc_local_plan failed: ") + neompc_last_error(mpc_));
-  }
-
-  geometry_msgs::msg::TwistStamped cmd_vel_final;
+  geometry_msgs::msg::TwistStamped cmd_vel_final;                                     // cpp:250-254
   cmd_vel_final.header.frame_id = costmap_ros_->getBaseFrameID();
   cmd_vel_final.twist.linear.x = last_response_.vx;
   cmd_vel_final.twist.linear.y = last_response_.vy;
   cmd_vel_final.twist.angular.z = last_response_.omega;
   return cmd_vel_final;
+}
+
+// The predicted path the Python server published on 'local_plan' (publishLocalPlan, srv.py:271-310, called :365): computed
+// on demand from the last solve.
+const std::vector<neompc_plan_pose> & NeoMpcPlanner::lastLocalPlan() {
+  std::lock_guard<std::mutex> lock(mutex_);
+  if (!local_plan_valid_ && mpc_) {
+    last_local_plan_.resize((size_t)params_.control_steps + 1);
+    if (neompc_local_plan(mpc_, &last_request_, last_plan_.data(), 1, last_local_plan_.data()) != NEOMPC_OK)
+      throw nav2_core::ControllerException(std::string("neompc_local_plan failed: ") + neompc_last_error(mpc_));
+    local_plan_valid_ = true;
+  }
+  return last_local_plan_;
 }
 
 }  // namespace neo_mpc_planner

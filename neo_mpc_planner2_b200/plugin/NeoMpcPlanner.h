@@ -6,6 +6,7 @@
 #ifndef NEO_MPC_PLANNER2_B200_PLUGIN_NEOMPCPLANNER_H_
 #define NEO_MPC_PLANNER2_B200_PLUGIN_NEOMPCPLANNER_H_
 
+#include <cstdint>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -45,11 +46,13 @@ public:
   // diagnostics of the last solve (what the reference published as local_plan, srv.py:365)
   const std::vector<float> & lastPlan() const { return last_plan_; }
   const neompc_response & lastResponse() const { return last_response_; }
-  const std::vector<neompc_plan_pose> & lastLocalPlan() const { return last_local_plan_; }   // poses of /mpc_local_plan
+  const std::vector<neompc_plan_pose> & lastLocalPlan();       // poses of the 'local_plan' topic (srv.py:107), on demand
+  const neompc_request & lastRequest() const { return last_request_; }      // the Optimizer request of the last tick (cpp:240-246)
+  const neompc_carrot_info & lastCarrotInfo() const { return last_info_; }  // closest pose, carrot index, flags of the last tick
+  bool lastTickUploadedCostmap() const { return last_upload_; }
 
 private:
-  geometry_msgs::msg::PoseStamped pickCarrot(const geometry_msgs::msg::PoseStamped & robot, double lookahead);
-  void uploadCostmap();
+  bool uploadCostmapIfChanged();
 
   rclcpp_lifecycle::LifecycleNode::WeakPtr node_;
   std::shared_ptr<tf2_ros::Buffer> tf_;
@@ -60,6 +63,8 @@ private:
   nav_msgs::msg::Path global_plan_;
   geometry_msgs::msg::Pose goal_pose_;
   bool closer_to_goal_ = false;
+  bool slow_down_ = true;                // reference h:162
+  uint32_t plan_start_ = 0;              // first plan pose not yet pruned (the reference erases the ones before, cpp:127)
   double lookahead_dist_min_ = 0.5, lookahead_dist_max_ = 0.5, lookahead_dist_close_to_goal_ = 0.5;
   double control_frequency_ = 20.0;
   double last_call_time_ = 0.0;          // srv.py:138
@@ -68,6 +73,14 @@ private:
   std::vector<float> last_plan_;
   std::vector<neompc_plan_pose> last_local_plan_;
   neompc_response last_response_{};
+  neompc_request last_request_{};
+  neompc_carrot_info last_info_{};
+  bool local_plan_valid_ = false, last_upload_ = false;
+  // what the device holds of the costmap (uploadCostmapIfChanged)
+  bool costmap_loaded_ = false;
+  uint64_t costmap_sum_ = 0;
+  unsigned costmap_w_ = 0, costmap_h_ = 0;
+  double costmap_res_ = 0.0, costmap_ox_ = 0.0, costmap_oy_ = 0.0;
   std::mutex mutex_;
 };
 

@@ -1,6 +1,7 @@
 // Stand-in for nav2_costmap_2d::Costmap2D / Costmap2DROS: a raw 0..254 grid plus the robot footprint.
 #pragma once
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "geometry_msgs/msg/types.hpp"
@@ -15,8 +16,10 @@ public:
   double getResolution() const { return res_; }
   double getOriginX() const { return ox_; }
   double getOriginY() const { return oy_; }
+  typedef std::recursive_mutex mutex_t;                      // as in nav2_costmap_2d::Costmap2D
+  mutex_t * getMutex() { return &mutex_; }
 private:
-  unsigned w_, h_; double res_, ox_, oy_; std::vector<unsigned char> cells_;
+  unsigned w_, h_; double res_, ox_, oy_; std::vector<unsigned char> cells_; mutex_t mutex_;
 };
 class Costmap2DROS {
 public:

@@ -153,6 +153,7 @@ class BatchSolver:
     def comm_unique_id():
         """128 opaque bytes rank 0 creates and the caller distributes (neompc_comm_unique_id)."""
         lib = _lib.load()
+        _lib.prefer_torch_nccl()
         buf = (ctypes.c_ubyte * 128)()
         rc = lib.neompc_comm_unique_id(buf)
         if rc != 0:
@@ -160,6 +161,7 @@ class BatchSolver:
         return bytes(buf)
 
     def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        _lib.prefer_torch_nccl()
         buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self._lib.neompc_comm_init(self._h, buf, int(n_ranks), int(rank)), "neompc_comm_init")
 
@@ -218,6 +220,25 @@ class BatchSolver:
                                                     int(first_instance_id), _ptr(reqs), _ptr(info)),
                     "neompc_build_requests")
         return reqs, info
+
+    def control_tick(self, ticks, carrot_params, first_instance_id=STATELESS, want_plan=False, want_requests=False):
+        """neompc_control_tick: carrot selection + solve for n robots in one call.  Returns (responses, carrot info[, plan]
+        [, requests])."""
+        ticks = np.ascontiguousarray(ticks, dtype=TICK_DTYPE)
+        n = len(ticks)
+        out = np.empty(n, RESPONSE_DTYPE)
+        info = np.empty(n, CARROT_INFO_DTYPE)
+        plan = np.empty((n, 3 * self.control_steps), np.float32) if want_plan else None
+        reqs = np.empty(n, REQUEST_DTYPE) if want_requests else None
+        rc = self._lib.neompc_control_tick(self._h, _ptr(carrot_params), _ptr(ticks), n, int(first_instance_id), _ptr(out),
+                                           _ptr(info), _ptr(reqs), _ptr(plan))
+        self._check(rc, "neompc_control_tick")
+        res = [out, info]
+        if want_plan:
+            res.append(plan)
+        if want_requests:
+            res.append(reqs)
+        return tuple(res)
 
     def build_requests_device(self, carrot_params, d_ticks, n, d_reqs, d_info, first_instance_id=STATELESS, stream=None):
         if stream == 0:
