@@ -69,6 +69,7 @@ def test_build_requests_matches_oracle(encoding):
         s.set_footprint(wl.footprint)
         s.set_plan(plan)
         cp = s.carrot_params(*[float(v) for v in la], controller_frequency=30.0)
+        s.reserve_instances(100 + len(ticks))                          # ids 100 .. 100 + n - 1 need their state rows
         reqs, info = s.build_requests(ticks, cp, first_instance_id=100)
         out = s.solve(np.where(True, reqs, reqs))                      # the requests feed the solver as they are
     mtd = max(cells.shape) * wl.resolution / 2.0
