@@ -216,6 +216,9 @@ int neompc_get_state(neompc_handle* h, uint32_t id, float* initial_guess, float 
  * (the "x.x" of srv.py:363 before the low-pass), e.g. to publish local_plan (srv.py:271-310). */
 int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n,
                        neompc_response* out, float* plan_or_null);
+/* Same, but only the answer a controller needs comes back: twist_out = n * 3 floats (vx, vy, omega), i.e. the
+ * Optimizer response's output_vel (cpp:252) without the diagnostics — 12 instead of 32 bytes per problem over PCIe.  A stopped robot (srv.py:374-377) is the zero twist. */
+int neompc_solve_batch_twists(neompc_handle* h, const neompc_request* reqs, size_t n, float* twist_out);
 /* Device buffers, asynchronous on `stream` (a cudaStream_t; NULL = the handle's own stream).
  * twist_or_null: n*3 floats (vx,vy,omega) packed — the payload of the multi-GPU gather. */
 int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, size_t n,

@@ -20,7 +20,7 @@ EXPORTS = [
     "neompc_eval_objective", "neompc_launch_count", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
     "neompc_comm_unique_id", "neompc_comm_init", "neompc_comm_init_all", "neompc_comm_destroy", "neompc_comm_info",
     "neompc_shard_rows", "neompc_solve_gather_device", "neompc_gather_wait", "neompc_fleet_solve",
-    "neompc_fleet_get_gathered", "neompc_control_tick",
+    "neompc_fleet_get_gathered", "neompc_control_tick", "neompc_solve_batch_twists",
 ]
 
 _lib = None
@@ -79,6 +79,7 @@ def load():
     lib.neompc_reset_state.argtypes = [vp, vp, sz]
     lib.neompc_get_state.argtypes = [vp, u32, vp, vp, vp, vp]
     lib.neompc_solve_batch.argtypes = [vp, vp, sz, vp, vp]
+    lib.neompc_solve_batch_twists.argtypes = [vp, vp, sz, vp]
     lib.neompc_solve_batch_device.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     lib.neompc_solve_msgs.argtypes = [vp, vp, sz, vp, vp]
     lib.neompc_pack_requests.argtypes = [vp, vp, sz, vp, vp]

@@ -86,6 +86,7 @@ struct SolverConst {
   int pad4, pitch4;       // its padding and row pitch
   int pad_ok;             // 1: the padding covers twice a plan's reach -> the solver samples without bounds tests
   float k_lethal;         // lut_cost entry of the lethal byte (unique to it: build_tables)
+  int polish_max;         // guidance: iteration cap of the second phase
   float sur_tol;          // guidance: the first phase stops at sur_tol x the tolerances of the second
   float cm_curv;          // curvature floor of the guided costmap term in the preconditioner (Solver::init)
   int guided;             // 1: the solve starts on the interpolated costmap term (costmap guidance, Solver::sur)
@@ -843,6 +844,7 @@ struct Solver {
   float u[S][3], g[S][3], pg[S][3];
   float f, pgmax;
   unsigned iters, evals, status;
+  unsigned iters_sw;     // guidance: iteration count at the switch to the second phase
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
   bool sur;              // costmap guidance: this solve is still on the interpolated costmap term (phase 1 of 2)
@@ -899,7 +901,7 @@ struct Solver {
       }
     }
     f = 0.0f; pgmax = 0.0f;
-    iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER;
+    iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER; iters_sw = 0xffffffffu;
     hist_len = 0; head = 0; small_steps = 0;
     active = valid; force_pg = true; plain = false; first = true;
   }
@@ -1121,12 +1123,17 @@ struct Solver {
       // ---- convergence test on the projected gradient  pg = x - Proj(x - g)
       if (active && pgmax <= (sur ? P.sur_tol : 1.0f) * P.tol_pg) { active = false; status = NEOMPC_STATUS_CONVERGED; }
       if (active && (int)iters >= P.max_iter) { active = false; status = NEOMPC_STATUS_MAXITER; }
+      // the second phase of a guided solve refines a point that is already within a cell of its optimum: bounded
+      if (active && !first && iters_sw != 0xffffffffu && iters - iters_sw >= (unsigned)P.polish_max) {
+        active = false; status = NEOMPC_STATUS_CONVERGED;
+      }
     }
     first = false;
     // Costmap guidance, end of the first phase: the guided solve has settled on the interpolated costmap term; the solve
     // continues from that point on the reference's objective (the next pass re-evaluates the point there).
     if (sur && !active && has_instance && status != NEOMPC_STATUS_MAXITER) {
       sur = false;
+      iters_sw = iters;
       active = true; first = true; force_pg = true; plain = false;
       hist_len = 0; head = 0; small_steps = 0;
       status = NEOMPC_STATUS_MAXITER;

@@ -108,6 +108,7 @@ constexpr float kFScale = 4e-3f;
 constexpr float kXScale = 0.2f;
 constexpr float kCmCurvature = 0.02f;   // SolverConst::cm_curv
 constexpr float kGuidedTolScale = 2.0f;  // SolverConst::sur_tol
+constexpr int kPolishMaxIterations = 1000; // SolverConst::polish_max
       // SolverConst::skip_polish in units of opt_tolerance
 
 inline void build_const(const neompc_params& p, SolverConst& c) {
@@ -158,6 +159,7 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.k_lethal = lethal_entry(p);
   c.cm_curv = kCmCurvature;
   c.sur_tol = kGuidedTolScale;
+  c.polish_max = kPolishMaxIterations;
   c.guided = (p.costmap_guidance == NEOMPC_GUIDANCE_ON && p.costmap_mode == NEOMPC_COSTMAP_NEAREST) ? 1 : 0;
   c.state = nullptr;
   c.state_stride = state_stride_for(N);

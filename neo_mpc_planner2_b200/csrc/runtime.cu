@@ -44,6 +44,8 @@ struct neompc_handle {
   neompc_request* d_reqs = nullptr;
   neompc_response* d_resp = nullptr;
   float* d_plan = nullptr;
+  float* d_twist = nullptr;         // staging of neompc_solve_batch_twists
+  size_t cap_twist = 0;
   neompc_optimizer_request* d_msgs = nullptr;
   size_t cap_reqs = 0, cap_plan = 0, cap_msgs = 0;
   uint64_t launches = 0;
@@ -506,7 +508,7 @@ int neompc_destroy(neompc_handle* h) {
   comm_release(h);
   cudaFree(h->d_gather);
   cudaFree(h->d_lut_cost); cudaFree(h->d_lut_flag); cudaFree(h->d_cells); cudaFree(h->d_cells4); cudaFree(h->d_state);
-  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs);
+  cudaFree(h->d_reqs); cudaFree(h->d_resp); cudaFree(h->d_plan); cudaFree(h->d_msgs); cudaFree(h->d_twist);
   cudaFree(h->d_path); cudaFree(h->d_raw_table); cudaFree(h->d_ticks); cudaFree(h->d_info);
   cudaFreeHost(h->err_word); cudaFreeHost(h->mb_msgs); cudaFreeHost(h->mb_reqs); cudaFreeHost(h->mb_resp); cudaFreeHost(h->mb_plan); cudaFreeHost(h->mb_ticks); cudaFreeHost(h->mb_info);
   delete h;
@@ -675,15 +677,20 @@ int neompc_solve_batch_device(neompc_handle* h, const neompc_request* d_reqs, si
   return do_solve_device(h, d_reqs, n, d_out, d_twist_or_null, d_plan_or_null, s);
 }
 
-int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, neompc_response* out,
-                       float* plan_or_null) {
-  if (!h || (n > 0 && (!reqs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
-  if (n == 0) return NEOMPC_OK;
-  NEOMPC_DEVICE(h);
+// Host buffers in, host buffers out.  out: full responses (or null), twist_out: packed (vx, vy, omega) (or null).
+static int solve_batch_host(neompc_handle* h, const neompc_request* reqs, size_t n, neompc_response* out, float* twist_out,
+                            float* plan_or_null) {
   int rc = check_unique_ids(h, reqs, n);
   if (rc != NEOMPC_OK) return rc;
   rc = ensure_staging(h, n, plan_or_null != nullptr, false);
   if (rc != NEOMPC_OK) return rc;
+  if (twist_out && n * 3 > h->cap_twist) {
+    NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_twist);
+    h->d_twist = nullptr; h->cap_twist = 0;
+    NEOMPC_CUDA(h, cudaMalloc(&h->d_twist, n * 3 * sizeof(float)));
+    h->cap_twist = n * 3;
+  }
   if (n <= kMailboxRequests) {                 // small batch: pinned mailbox in, mapped mailbox out (see solve_msgs)
     const size_t n3s = n * 3 * (size_t)h->params.control_steps;
     std::memcpy(h->mb_reqs, reqs, n * sizeof(neompc_request));
@@ -691,18 +698,22 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
     rc = do_solve_device(h, h->d_reqs, n, h->mb_resp, nullptr, plan_or_null ? h->mb_plan : nullptr, h->stream);
     if (rc != NEOMPC_OK) return rc;
     NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
-    std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
+    if (out) std::memcpy(out, h->mb_resp, n * sizeof(neompc_response));
+    if (twist_out)
+      for (size_t i = 0; i < n; ++i) {
+        twist_out[3 * i] = h->mb_resp[i].vx; twist_out[3 * i + 1] = h->mb_resp[i].vy; twist_out[3 * i + 2] = h->mb_resp[i].omega;
+      }
     if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3s * sizeof(float));
     return check_state_errors(h);
   }
-  // Large batches are cut into two chunks on two streams, so the H2D copy of one chunk, the solve of
-  // the other and the D2H copies overlap (the copy engines for the two directions and the SMs are independent).
-  // Problems are independent, so chunking does not change any result.
+  // Large batches are cut into chunks on two streams, so the H2D copy of one chunk, the solve of another and the D2H
+  // copies overlap (the copy engines for the two directions and the SMs are independent).  Problems are independent, so
+  // chunking does not change any result.  What stays exposed is the H2D of the first chunk and the D2H of the last one.
+  // Three chunks: measured on C3 with the board at its working clocks (profiles/host_chunks_r2.txt), 65536 requests in
+  // 0.664 / 0.624 / 0.611 / 0.641 / 0.653 / 0.771 ms with 1 / 2 / 3 / 4 / 6 / 8 chunks (kernel alone 0.55 ms).
   const size_t n3 = 3 * (size_t)h->params.control_steps;
   static const int chunk_override = std::getenv("NEOMPC_CHUNKS") ? std::atoi(std::getenv("NEOMPC_CHUNKS")) : 0;   // tuning knob
-  // two chunks: as fast as four on a quiet host (0.452 vs 0.455 ms per 65536 requests) and much less sensitive to a busy
-  // one, where every extra enqueue costs (0.459 vs 0.596 ms; profiles/host_chunks_r1.txt)
-  const int chunks = n >= 16384 ? (chunk_override > 0 ? chunk_override : 2) : 1;
+  const int chunks = n >= 16384 ? (chunk_override > 0 ? chunk_override : 3) : 1;
   const size_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
   cudaStream_t streams[2] = {h->stream, chunks > 1 ? h->stream2 : h->stream};
   for (int c = 0; c < chunks; ++c) {
@@ -711,9 +722,13 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
     const size_t cnt = n - lo < per ? n - lo : per;
     cudaStream_t s = streams[c & 1];
     NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs + lo, reqs + lo, cnt * sizeof(neompc_request), cudaMemcpyHostToDevice, s));
-    rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, nullptr, plan_or_null ? h->d_plan + lo * n3 : nullptr, s, n);
+    rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, twist_out ? h->d_twist + lo * 3 : nullptr,
+                         plan_or_null ? h->d_plan + lo * n3 : nullptr, s, n);
     if (rc != NEOMPC_OK) return rc;
-    NEOMPC_CUDA(h, cudaMemcpyAsync(out + lo, h->d_resp + lo, cnt * sizeof(neompc_response), cudaMemcpyDeviceToHost, s));
+    if (out)
+      NEOMPC_CUDA(h, cudaMemcpyAsync(out + lo, h->d_resp + lo, cnt * sizeof(neompc_response), cudaMemcpyDeviceToHost, s));
+    if (twist_out)
+      NEOMPC_CUDA(h, cudaMemcpyAsync(twist_out + lo * 3, h->d_twist + lo * 3, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (plan_or_null)
       NEOMPC_CUDA(h, cudaMemcpyAsync(plan_or_null + lo * n3, h->d_plan + lo * n3, cnt * n3 * sizeof(float),
                                      cudaMemcpyDeviceToHost, s));
@@ -721,6 +736,21 @@ int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, n
   NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
   if (chunks > 1) NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream2));
   return check_state_errors(h);
+}
+
+int neompc_solve_batch(neompc_handle* h, const neompc_request* reqs, size_t n, neompc_response* out,
+                       float* plan_or_null) {
+  if (!h || (n > 0 && (!reqs || !out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_DEVICE(h);
+  return solve_batch_host(h, reqs, n, out, nullptr, plan_or_null);
+}
+
+int neompc_solve_batch_twists(neompc_handle* h, const neompc_request* reqs, size_t n, float* twist_out) {
+  if (!h || (n > 0 && (!reqs || !twist_out))) return fail(h, NEOMPC_ERR_INVALID, "null argument");
+  if (n == 0) return NEOMPC_OK;
+  NEOMPC_DEVICE(h);
+  return solve_batch_host(h, reqs, n, nullptr, twist_out, nullptr);
 }
 
 int neompc_pack_requests(neompc_handle* h, const neompc_optimizer_request* d_msgs, size_t n, neompc_request* d_reqs,

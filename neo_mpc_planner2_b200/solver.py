@@ -138,6 +138,19 @@ class BatchSolver:
         self._check(self._lib.neompc_solve_batch(self._h, ctypes.c_void_p(reqs_ptr), int(n), ctypes.c_void_p(out_ptr),
                                                  ctypes.c_void_p(plan_ptr) if plan_ptr else None), "neompc_solve_batch")
 
+    def solve_twists(self, reqs, out=None):
+        """neompc_solve_batch_twists: host requests in, [n, 3] (vx, vy, omega) out."""
+        reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DTYPE)
+        n = len(reqs)
+        if out is None:
+            out = np.empty((n, 3), np.float32)
+        self._check(self._lib.neompc_solve_batch_twists(self._h, _ptr(reqs), n, _ptr(out)), "neompc_solve_batch_twists")
+        return out
+
+    def solve_twists_raw(self, reqs_ptr, n, twist_ptr):
+        self._check(self._lib.neompc_solve_batch_twists(self._h, ctypes.c_void_p(reqs_ptr), int(n), ctypes.c_void_p(twist_ptr)),
+                    "neompc_solve_batch_twists")
+
     def solve_device(self, d_reqs, n, d_out, d_twist=None, d_plan=None, stream=None):
         """Device pointers (ints) in and out, asynchronous on `stream`: a cudaStream_t as int (0 = the legacy default
         stream, which CUDA names by the handle 0x1), or None for the handle's own stream."""

@@ -612,3 +612,15 @@ def test_duplicate_instance_ids_debug_check(Solver, monkeypatch):
         s.reserve_instances(8)
         with pytest.raises(NeompcError, match="duplicate instance_id"):
             s.solve(req)
+
+
+@pytest.mark.parametrize("n_total", [40, 40001])
+def test_twists_entry_equals_full_responses(Solver, n_total):
+    """neompc_solve_batch_twists returns exactly the (vx, vy, omega) of neompc_solve_batch (mailbox and chunked paths)."""
+    wl, p, cm = setup_workload("c3", n_total, 10)
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        full = s.solve(wl.requests)
+        tw = s.solve_twists(wl.requests)
+    want = np.stack([full["vx"], full["vy"], full["omega"]], axis=1)
+    assert tw.tobytes() == want.tobytes()
