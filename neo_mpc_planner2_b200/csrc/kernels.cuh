@@ -78,7 +78,7 @@ __device__ __forceinline__ neompc_request load_request(const neompc_request* req
 
 // resident blocks per SM the register allocator is asked to allow (65536 regs / (128 threads * blocks))
 #ifndef NEOMPC_MINBLOCKS_S2
-#define NEOMPC_MINBLOCKS_S2 5
+#define NEOMPC_MINBLOCKS_S2 4
 #endif
 // NEOMPC_MINBLOCKS_RAW_S3: resident blocks of kBlockThreads (64) per SM the S = 3 kernels are compiled for, unscaled.
 // 7 instead of 8: ptxas still allocates 128 registers (8 blocks stay resident) but schedules differently — measured

@@ -802,7 +802,7 @@ NEOMPC_HD bool footprint_lethal(const SolverConst& P, const CostTables& T, doubl
 // Per pair p (0..m-1): [3S floats s][3S floats y][rho][alpha scratch of the two-loop recursion]
 // ---------------------------------------------------------------------------------------------------------
 template <int S>
-NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2) + 2 * S; }   // pairs + (av, aw) of precondition()
+NEOMPC_HD int hist_floats_per_lane(int m) { return m * (6 * S + 2) + 2 * S + 6 * S; }   // pairs + (av, aw) of precondition() + pg + g
 
 template <int S, bool X>
 NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], const float (*g)[3], float (*pg)[3]) {
@@ -841,13 +841,23 @@ struct Solver {
   Instance I;
   bool fp_hit, has_instance;
   // iterate
-  float u[S][3], g[S][3], pg[S][3];
+  float u[S][3];                 // (gradient and projected gradient of the iterate live in shared memory: g_at(), pg_at())
   float f, pgmax;
   unsigned iters, evals, status;
   unsigned iters_sw;     // guidance: iteration count at the switch to the second phase
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
   bool sur;              // costmap guidance: this solve is still on the interpolated costmap term (phase 1 of 2)
+
+  // projected gradient at the current iterate, element e of this lane (kept in shared memory behind the history and the
+  // preconditioner constants: 3S registers fewer across the whole pass)
+  static NEOMPC_HD float* pg_at(const SolverConst& P, float* hist, int stride) {
+    return hist + (size_t)((X ? P.m : 1) * PAIR + 2 * S) * stride;
+  }
+
+  static NEOMPC_HD float* g_at(const SolverConst& P, float* hist, int stride) {
+    return hist + (size_t)((X ? P.m : 1) * PAIR + 5 * S) * stride;
+  }
 
   NEOMPC_HD void prologue(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid, int lg,
                           float* hist, int stride) {
@@ -875,12 +885,11 @@ struct Solver {
       u[j][1] = ld ? row[3 * i + 1] : 0.0f;
       u[j][2] = ld ? row[3 * i + 2] : 0.0f;
       project_step<X>(P, u[j][0], u[j][1], u[j][2]);
-      NEOMPC_UNROLL
-      for (int q = 0; q < 3; ++q) { g[j][q] = 0.0f; pg[j][q] = 0.0f; }
     }
     sur = P.guided != 0 && P.cells4 != nullptr && !(X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR);
     const int m = X ? P.m : 1;                     // the fast path is dispatched only for one history pair
     for (int e = 0; e < m * PAIR; ++e) hist[(size_t)e * stride] = 0.0f;
+    for (int e = 0; e < 6 * S; ++e) pg_at(P, hist, stride)[(size_t)e * stride] = 0.0f;       // pg and g
     {
       float* tab = hist + (size_t)(m * PAIR) * stride;               // tracking-term majorants of precondition()
       const float dt2 = 2.0f * P.dt * P.dt;
@@ -944,7 +953,10 @@ struct Solver {
     // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
     const bool use_qn = !first && !force_pg && hist_len > 0;
     NEOMPC_UNROLL
-    for (int j = 0; j < S; ++j) { r[j][0] = pg[j][0]; r[j][1] = pg[j][1]; r[j][2] = pg[j][2]; }
+    float* const pgs = pg_at(P, hist, stride);
+    float* const gsm = g_at(P, hist, stride);
+    NEOMPC_UNROLL
+    for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] = pgs[(size_t)e * stride];
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -986,9 +998,11 @@ struct Solver {
     for (int j = 0; j < S; ++j) {
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) {
+        const float pv = pgs[(size_t)(3 * j + q) * stride];
         d[j][q] = -r[j][q];
-        gd += pg[j][q] * d[j][q];
-        pgn2 += pg[j][q] * pg[j][q];
+        r[j][q] = pv;                            // (r is free from here on: keeps pg for the fallback direction below)
+        gd += pv * d[j][q];
+        pgn2 += pv * pv;
       }
     }
     gd = Grp<G>::sum(gd);
@@ -1001,7 +1015,7 @@ struct Solver {
       NEOMPC_UNROLL
       for (int j = 0; j < S; ++j) {
         const float n2 = u[j][0] * u[j][0] + u[j][1] * u[j][1];
-        const float gr = g[j][0] * u[j][0] + g[j][1] * u[j][1];
+        const float gr = gsm[(size_t)(3 * j) * stride] * u[j][0] + gsm[(size_t)(3 * j + 1) * stride] * u[j][1];
         const bool bind = n2 >= P.R * P.R * (1.0f - 2e-6f) && gr < 0.0f;
         const float dr = div_approx(d[j][0] * u[j][0] + d[j][1] * u[j][1], fmaxf(n2, 1e-30f));
         d[j][0] -= bind ? dr * u[j][0] : 0.0f;
@@ -1010,14 +1024,15 @@ struct Solver {
     }
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
-      const bool at_lo = u[j][2] <= P.lo[2] && g[j][2] > 0.0f;
-      const bool at_hi = u[j][2] >= P.hi[2] && g[j][2] < 0.0f;
+      const float gw = gsm[(size_t)(3 * j + 2) * stride];
+      const bool at_lo = u[j][2] <= P.lo[2] && gw > 0.0f;
+      const bool at_hi = u[j][2] >= P.hi[2] && gw < 0.0f;
       d[j][2] = (at_lo || at_hi) ? 0.0f : d[j][2];
     }
     float alpha = 1.0f;
     if (!qn_dir) {
       NEOMPC_UNROLL
-      for (int j = 0; j < S; ++j) { d[j][0] = -pg[j][0]; d[j][1] = -pg[j][1]; d[j][2] = -pg[j][2]; }
+      for (int j = 0; j < S; ++j) { d[j][0] = -r[j][0]; d[j][1] = -r[j][1]; d[j][2] = -r[j][2]; }
       // first trial moves the largest component by about the velocity range
       alpha = fmaxf(1.0f, div_approx(P.R, fmaxf(pgmax, 1e-12f)));
     }
@@ -1034,7 +1049,8 @@ struct Solver {
         xt[j][1] = u[j][1] + alpha * d[j][1];
         xt[j][2] = u[j][2] + alpha * d[j][2];
         project_step<X>(P, xt[j][0], xt[j][1], xt[j][2]);
-        gs += g[j][0] * (xt[j][0] - u[j][0]) + g[j][1] * (xt[j][1] - u[j][1]) + g[j][2] * (xt[j][2] - u[j][2]);
+        gs += gsm[(size_t)(3 * j) * stride] * (xt[j][0] - u[j][0]) + gsm[(size_t)(3 * j + 1) * stride] * (xt[j][1] - u[j][1]) +
+              gsm[(size_t)(3 * j + 2) * stride] * (xt[j][2] - u[j][2]);
       }
       gs = Grp<G>::sum(gs);
       const float ftrial = Grp<G>::sum(fw.template run<false>(P, T, I, xt, lg, sur));
@@ -1058,7 +1074,8 @@ struct Solver {
                  (int)qn_dir, alpha, (int)accepted, ft, evals, hist_len);
     for (int j = 0; j < S; ++j)
       NEOMPC_TRACE("      u %+.4f %+.4f %+.4f   pg %+.2e %+.2e %+.2e  g %+.2e %+.2e %+.2e  d %+.2e %+.2e %+.2e\n", u[j][0],
-                   u[j][1], u[j][2], pg[j][0], pg[j][1], pg[j][2], g[j][0], g[j][1], g[j][2], d[j][0], d[j][1], d[j][2]);
+                   u[j][1], u[j][2], pgs[(size_t)(3 * j) * stride], pgs[(size_t)(3 * j + 1) * stride], pgs[(size_t)(3 * j + 2) * stride],
+                   gsm[(size_t)(3 * j) * stride], gsm[(size_t)(3 * j + 1) * stride], gsm[(size_t)(3 * j + 2) * stride], d[j][0], d[j][1], d[j][2]);
 
     // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
     float gn[S][3], pgn[S][3];
@@ -1071,7 +1088,7 @@ struct Solver {
     for (int j = 0; j < S; ++j) {
       NEOMPC_UNROLL
       for (int q = 0; q < 3; ++q) {
-        const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pg[j][q];
+        const float sv = xt[j][q] - u[j][q], yv = pgn[j][q] - pgs[(size_t)(3 * j + q) * stride];
         sy += sv * yv; yy += yv * yv;
         smax = fmaxf(smax, fabsf(sv));
         d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
@@ -1097,7 +1114,11 @@ struct Solver {
         NEOMPC_UNROLL
         for (int j = 0; j < S; ++j) {
           NEOMPC_UNROLL
-          for (int q = 0; q < 3; ++q) { u[j][q] = xt[j][q]; g[j][q] = gn[j][q]; pg[j][q] = pgn[j][q]; }
+          for (int q = 0; q < 3; ++q) {
+            u[j][q] = xt[j][q];
+            gsm[(size_t)(3 * j + q) * stride] = gn[j][q];
+            pgs[(size_t)(3 * j + q) * stride] = pgn[j][q];
+          }
         }
         f = ft;
         pgmax = pgmax_n;

@@ -172,11 +172,12 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
 // c(S): warp instructions of one solver pass with S steps per lane (kernels exist for S <= 4; more steps per lane spill registers); shuffles(G): scans and
 // reductions take ceil(log2 G) exchange steps, and a group size that is not a power of two pays ~20 % on top (scan +
 // broadcast instead of butterflies, computed source lanes); lockstep: the groups of a warp wait for the slowest one,
-// which costs more the more groups there are.  Measured: N=10 (4,3) 0.458 ms = (5,2) 0.459 ms, (8,2) 0.537;
-// N=20 (8,3) 1.66 ms, (10,2) 1.73, (16,2) 2.04, (5,4) 2.09; N=3 (1,3) 0.168 ms, (2,2) 0.182, (3,1) 0.200.
+// which costs more the more groups there are.  Measured in round 2 (guided solve, profiles/tiling_sweep_r2.txt):
+// N=10 (5,2) 0.542 ms, (4,3) 0.567, (8,2) 0.625; N=20 (10,2) 1.840 ms, (5,4) 1.842, (8,3) 1.856, (16,2) 2.131;
+// round 1, N=3 at throughput sizes: (1,3) 0.168 ms, (2,2) 0.182, (3,1) 0.200.
 constexpr int kGroupSizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 16, 32};
 inline double tiling_cost(int g, int s) {
-  static const double c[5] = {0.0, 0.35, 0.62, 1.0, 1.55};
+  static const double c[5] = {0.0, 0.35, 0.59, 1.0, 1.55};   // (S = 2 kernels run without spills at 120 registers since round 2)
   int lg2 = 0;
   while ((1 << lg2) < g) ++lg2;
   const bool pow2 = (g & (g - 1)) == 0;

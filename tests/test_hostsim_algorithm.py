@@ -150,7 +150,7 @@ def test_state_machine_sequences_on_host(golden):
 def test_lane_tiling_choice():
     """Host logic of the dispatcher (mpc_setup.h: choose_tiling / choose_latency_tiling): every horizon up to
     NEOMPC_MAX_CONTROL_STEPS gets a tiling the library instantiates (S <= 4, G from the supported set, G*S >= N); the
-    auto choice reproduces the measured winners (profiles/tiling_sweep_r1c.txt, _r1d.txt)."""
+    auto choice reproduces the measured winners (profiles/tiling_sweep_r2.txt)."""
     import ctypes
     from tests.hostsim import build
     lib = ctypes.CDLL(build())
@@ -169,7 +169,7 @@ def test_lane_tiling_choice():
             assert g in sizes and g >= lanes and 1 <= s <= 4 and g * s >= n, (n, lanes, g, s)
             if (n + lanes - 1) // lanes <= 4:
                 assert g == lanes
-    assert tiling(3) == (1, 3) and tiling(10) == (4, 3) and tiling(20) == (8, 3)
+    assert tiling(3) == (1, 3) and tiling(10) == (5, 2) and tiling(20) == (10, 2)
     assert tiling(10, latency=1) == (16, 1) and tiling(3, latency=1) == (4, 1) and tiling(64, latency=1) == (32, 2)
 
 
