@@ -463,6 +463,14 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         bytes_per_solve = wl.algorithmic_bytes_per_solve(n)
+        # what the round-2 kernel is expected to pull from HBM per launch: the requests + the corner-packed costmap copy
+        # (4 cells per 32-bit word, padded by twice a plan's reach)
+        import math
+        kernel_reads = n * REQUEST_DTYPE.itemsize
+        if wl.cells is not None:
+            reach = math.ceil(float(wl.params["max_vel_trans"]) * float(wl.params["prediction_horizon"]) / wl.resolution)
+            pad = 2 * reach + 6
+            kernel_reads += (wl.cells.shape[1] + 2 * pad) * (wl.cells.shape[0] + 2 * pad) * 4
         k_ms = float(np.mean(kern_ms))
         achieved = bytes_per_solve * n / (k_ms * 1e-3) / 1e9
         wl_name, _ = _workload_name(args.config)
@@ -478,7 +486,7 @@ def run_ours(args):
                 ach_issue = tr["inst_executed"] / (k_ms * 1e-3)  # instruction count of the committed capture / live time
                 issue = {"achieved_gwarp_inst_per_s": ach_issue / 1e9, "peak_gwarp_inst_per_s": peak_issue / 1e9,
                          "frac": ach_issue / peak_issue, "warp_inst_per_launch": tr["inst_executed"],
-                         "source": "inst_executed from profiles/solve_kernel_r1_summary.md (ncu), time measured live"}
+                         "source": "inst_executed from " + tr["source"].split(":")[0] + " (ncu), time measured live"}
         except Exception:
             pass
         line = {
@@ -490,7 +498,8 @@ def run_ours(args):
                     "costmap_guidance": "off (round-1 strategy)" if args.costmap_guidance else "on",
                     "gather": "overlapped with the next step's solve on a second stream" if world > 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n, "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_solve * n,
+                         "expected_kernel_reads_per_launch": int(kernel_reads), "kernel": f"solve_kernel<{G},{S}>", "kernel_ms": k_ms,
                          "bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
                          "issue_slots": issue,
                          "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
