@@ -392,13 +392,15 @@ int comm_prepare(neompc_handle* h, int n_ranks, int rank) {
   return NEOMPC_OK;
 }
 
-// The gather moves 12 B per solve (786 KB per rank at C3) while the next batch is being solved on the same SMs: NCCL is
-// held to a few CTAs so that it does not take SMs from the solve kernel (NEOMPC_NCCL_MAX_CTAS, default 2).
+// The gather moves 12 B per solve (786 KB per rank at C3) while the next batch is being solved on the same SMs.  Holding NCCL
+// to very few CTAs (NEOMPC_NCCL_MAX_CTAS) was measured and is NOT the default: with 2 CTAs the gather gets ~10 GB/s next to
+// a solve kernel that fills every SM and ends up on the critical path (4 GPUs, C3: step 0.580 ms against 0.566 ms with
+// NCCL's own choice; 4 / 8 / 16 CTAs: 0.569 / 0.569 / 0.564 — profiles/nccl_ctas_r2.txt).
 ncclResult_t comm_init_rank(const NcclApi* api, ncclComm_t* comm, int n_ranks, const ncclUniqueId& id, int rank) {
   if (api->CommInitRankConfig) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
     const char* e = std::getenv("NEOMPC_NCCL_MAX_CTAS");
-    const int ctas = e ? std::atoi(e) : 2;
+    const int ctas = e ? std::atoi(e) : 0;
     if (ctas > 0) { cfg.minCTAs = 1; cfg.maxCTAs = ctas; }
     return api->CommInitRankConfig(comm, n_ranks, id, rank, &cfg);
   }
