@@ -69,3 +69,29 @@ def test_committed_bench_line_has_the_contract_keys():
     k = d["clocks"]
     assert k["sm_mhz"] and k["sm_max_mhz"] and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["cost_residual"]["median"] <= 0.0 and d["cost_residual"]["max"] <= 5e-3
+
+
+def test_committed_round2_bench_line():
+    """profiles/bench_r2_c3_1gpu.json is the line bench.py printed on the B200 box in round 2: the contract keys, the e2e
+    through the twists entry (12 B per problem back), the reference arm on the unmodified reference, the sustained record."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_c3_1gpu.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+              "sustained", "cost_residual", "plugin_tick_latency"):
+        assert k in d, k
+    assert d["metric"] == "mpc_solves_per_sec" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
+    assert set(d["config"]) == {"workload", "batch_per_gpu", "control_steps", "opt_tolerance", "cold_start",
+                                "footprint_mode", "costmap_mode", "l2", "parallelism"} and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and c["oracle_port_value"] > c["value"]
+    e = d["e2e"]
+    n = d["config"]["batch_per_gpu"]
+    assert e["h2d_bytes_per_step"] == 64 * n and e["d2h_bytes_per_step"] == 12 * n and 0.85 * d["value"] < e["value"] < d["value"]
+    assert d["gpu_launches"] == d["steps"]
+    s = d["sustained"]
+    assert s["seconds"] >= 1.9 and not s["reasons"] and s["sm_mhz_median"] >= 0.95 * d["clocks"]["sm_max_mhz"]
+    cr = d["cost_residual"]
+    assert cr["max"] <= 0.0 and cr["p99"] <= 0.0 and cr["frac_worse_than_opt_tol"] == 0.0
+    assert cr["first_control_vs_tight_scipy_p90"] <= 1e-2 and cr["first_control_vs_tight_scipy_p99"] <= 3e-2
