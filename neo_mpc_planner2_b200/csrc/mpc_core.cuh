@@ -87,6 +87,7 @@ struct SolverConst {
   int pad_ok;             // 1: the padding covers twice a plan's reach -> the solver samples without bounds tests
   float k_lethal;         // lut_cost entry of the lethal byte (unique to it: build_tables)
   int polish_max;         // guidance: iteration cap of the second phase
+  float alpha_warm;       // guidance, second phase: first trial at min(1, alpha_warm x the last accepted arc parameter)
   float sur_tol;          // guidance: the first phase stops at sur_tol x the tolerances of the second
   float cm_curv;          // curvature floor of the guided costmap term in the preconditioner (Solver::init)
   int guided;             // 1: the solve starts on the interpolated costmap term (costmap guidance, Solver::sur)
@@ -845,6 +846,7 @@ struct Solver {
   float f, pgmax;
   unsigned iters, evals, status;
   unsigned iters_sw;     // guidance: iteration count at the switch to the second phase
+  float last_alpha;      // arc parameter of the last accepted step
   int hist_len, head, small_steps;
   bool active, force_pg, plain, first;
   bool sur;              // costmap guidance: this solve is still on the interpolated costmap term (phase 1 of 2)
@@ -910,7 +912,7 @@ struct Solver {
       }
     }
     f = 0.0f; pgmax = 0.0f;
-    iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER; iters_sw = 0xffffffffu;
+    iters = 0; evals = 0; status = NEOMPC_STATUS_MAXITER; iters_sw = 0xffffffffu; last_alpha = 1.0f;
     hist_len = 0; head = 0; small_steps = 0;
     active = valid; force_pg = true; plain = false; first = true;
   }
@@ -1036,6 +1038,10 @@ struct Solver {
       // first trial moves the largest component by about the velocity range
       alpha = fmaxf(1.0f, div_approx(P.R, fmaxf(pgmax, 1e-12f)));
     }
+    // Second phase of a guided solve: arcs end at cost steps, and the arc parameter that was accepted last time predicts
+    // the next one far better than the unit step does — the first trial is bounded by alpha_warm x it (evaluation slots per
+    // warp of C3 51 -> 44; applied to the first phase too it costs the C2 tail: profiles/solver_tuning_r2.txt)
+    if (iters_sw != 0xffffffffu && qn_dir) alpha = fminf(alpha, P.alpha_warm * last_alpha);
     if (first) alpha = 0.0f;                     // evaluate the start point itself
 
     // ---- Armijo backtracking along the projection arc (all groups of the warp in lock step)
@@ -1122,6 +1128,7 @@ struct Solver {
         }
         f = ft;
         pgmax = pgmax_n;
+        if (!first) last_alpha = alpha;
         if (!first) {
           ++iters;
           // secondary stop: the objective stopped moving (relative) for two accepted steps in a row
@@ -1154,7 +1161,7 @@ struct Solver {
     // continues from that point on the reference's objective (the next pass re-evaluates the point there).
     if (sur && !active && has_instance && status != NEOMPC_STATUS_MAXITER) {
       sur = false;
-      iters_sw = iters;
+      iters_sw = iters; last_alpha = 1.0f;
       active = true; first = true; force_pg = true; plain = false;
       hist_len = 0; head = 0; small_steps = 0;
       status = NEOMPC_STATUS_MAXITER;

@@ -109,6 +109,7 @@ constexpr float kXScale = 0.2f;
 constexpr float kCmCurvature = 0.02f;   // SolverConst::cm_curv
 constexpr float kGuidedTolScale = 2.0f;  // SolverConst::sur_tol
 constexpr int kPolishMaxIterations = 1000; // SolverConst::polish_max
+constexpr float kAlphaWarm = 4.0f;       // SolverConst::alpha_warm
       // SolverConst::skip_polish in units of opt_tolerance
 
 inline void build_const(const neompc_params& p, SolverConst& c) {
@@ -160,6 +161,7 @@ inline void build_const(const neompc_params& p, SolverConst& c) {
   c.cm_curv = kCmCurvature;
   c.sur_tol = kGuidedTolScale;
   c.polish_max = kPolishMaxIterations;
+  c.alpha_warm = kAlphaWarm;
   c.guided = (p.costmap_guidance == NEOMPC_GUIDANCE_ON && p.costmap_mode == NEOMPC_COSTMAP_NEAREST) ? 1 : 0;
   c.state = nullptr;
   c.state_stride = state_stride_for(N);

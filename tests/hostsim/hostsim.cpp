@@ -48,6 +48,7 @@ void make_env(Env& e, const neompc_params* p, const uint8_t* cells, int W, int H
   if (getenv("HOSTSIM_PINALPHA")) e.c.pin_alpha = atof(getenv("HOSTSIM_PINALPHA"));
   if (getenv("HOSTSIM_CMCURV")) e.c.cm_curv = atof(getenv("HOSTSIM_CMCURV"));
   if (getenv("HOSTSIM_POLISHMAX")) e.c.polish_max = atoi(getenv("HOSTSIM_POLISHMAX"));
+  if (getenv("HOSTSIM_ALPHAWARM")) e.c.alpha_warm = atof(getenv("HOSTSIM_ALPHAWARM"));
   if (getenv("HOSTSIM_SURTOL")) e.c.sur_tol = atof(getenv("HOSTSIM_SURTOL"));
   if (getenv("HOSTSIM_PAIREPS")) e.c.pair_eps = atof(getenv("HOSTSIM_PAIREPS"));
   if (getenv("HOSTSIM_TOLX")) { e.c.tol_x = atof(getenv("HOSTSIM_TOLX")); e.c.pin_alpha = 0.0f; }
