@@ -109,15 +109,18 @@ bool NeoMpcPlanner::uploadCostmapIfChanged() {
   const unsigned w = cm->getSizeInCellsX(), h = cm->getSizeInCellsY();
   const unsigned char * cells = cm->getCharMap();
   const size_t bytes = (size_t)w * h;
-  uint64_t acc[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+  // eight independent lanes, rotate-xor-add mixing (no multiply on the critical path): memory-bound on a 1 MB costmap
+  uint64_t acc[8] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull,
+                     0x85EBCA77C2B2AE63ull, 0xD6E8FEB86659FD93ull, 0xA0761D6478BD642Full, 0xE7037ED1A0B428DBull};
   size_t i = 0;
-  for (; i + 32 <= bytes; i += 32) {
-    uint64_t v[4];
-    std::memcpy(v, cells + i, 32);
-    for (int k = 0; k < 4; ++k) acc[k] = (acc[k] ^ v[k]) * 0x100000001B3ull + (acc[k] >> 29);
+  for (; i + 64 <= bytes; i += 64) {
+    uint64_t v[8];
+    std::memcpy(v, cells + i, 64);
+    for (int k = 0; k < 8; ++k) { acc[k] ^= v[k]; acc[k] = ((acc[k] << 23) | (acc[k] >> 41)) + (acc[k] >> 17) + 0x9E3779B97F4A7C15ull; }
   }
-  for (; i < bytes; ++i) acc[i & 3] = (acc[i & 3] ^ cells[i]) * 0x100000001B3ull;
-  const uint64_t sum = acc[0] ^ (acc[1] << 1) ^ (acc[2] << 2) ^ (acc[3] << 3);
+  for (; i < bytes; ++i) acc[i & 7] = (((acc[i & 7] ^ cells[i]) << 23) | ((acc[i & 7] ^ cells[i]) >> 41)) + cells[i];
+  uint64_t sum = 0;
+  for (int k = 0; k < 8; ++k) sum = ((sum << 7) | (sum >> 57)) ^ (acc[k] * 0x100000001B3ull);
   const bool same = costmap_loaded_ && sum == costmap_sum_ && w == costmap_w_ && h == costmap_h_ &&
                     cm->getResolution() == costmap_res_ && cm->getOriginX() == costmap_ox_ && cm->getOriginY() == costmap_oy_;
   if (same) return false;
