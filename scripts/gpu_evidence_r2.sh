@@ -3,6 +3,7 @@
 set -u
 O=gpurun_out
 nproc > $O/nproc.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke.log 2>&1
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/r2_gpu_tests.log
 timeout 900 python bench.py > $O/r2_bench_c3.json 2> $O/r2_bench_c3.err
 for cfg in c2 c4 c5; do
