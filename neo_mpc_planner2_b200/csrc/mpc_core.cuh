@@ -144,12 +144,64 @@ NEOMPC_HD int state_stride_for(int n_steps) { return 3 * n_steps + kStateExtra; 
 // divide 32, e.g. G = 5: six groups, lanes 30-31 unused).  Powers of two use butterfly exchanges; other sizes run a
 // Hillis-Steele scan inside the group and broadcast the total from its last lane.  Either way every lane of a group
 // ends up with bit-identical scalars, so the lanes of a group always take the same decisions.
+// Groups whose size is not a power of two (G = 3, 5, 6, 10 — the production tilings (5,2) and (10,2) among them)
+// exchange through shared memory instead (NEOMPC_XCH, default on): every lane stores its value into the group's
+// 16-byte-aligned slot, the warp synchronises, and every lane reads ALL G values of its group back with vector loads
+// (G = 5: one LDS.128 + one LDS.32) and combines them locally in index order.  That is one store + two loads + four
+// adds where the shuffle scan needs four DEPENDENT shuffle round trips (~25 cycles each) — the dependency chain of a
+// collective drops from ~110 to ~45 cycles, which is what this issue/latency-bound kernel is short of.
+#ifndef NEOMPC_XCH
+#define NEOMPC_XCH 1
+#endif
+#ifndef NEOMPC_BLOCK_THREADS
+#define NEOMPC_BLOCK_THREADS 64
+#endif
+constexpr int kXchMaxWarps = NEOMPC_BLOCK_THREADS / 32;   // warps per block (kernels.cuh launches exactly this block size)
+constexpr int kXchMaxVals = 3;         // scalars exchanged by one collective at most
+
 template <int G>
 struct Grp {
   static constexpr bool kPow2 = (G & (G - 1)) == 0;
   static constexpr int kPerWarp = 32 / G;          // groups (= instances) per warp
+  static constexpr bool kXch = NEOMPC_XCH && !kPow2;
+  static constexpr int kSlot = (G + 3) & ~3;       // floats per group slot of the exchange buffer (16-byte aligned)
+  static constexpr int kSlots = (32 + G - 1) / G;  // incl. the partial group of leftover lanes
 #if defined(__CUDA_ARCH__)
   static __device__ __forceinline__ int lane() { return (int)(threadIdx.x & 31u); }
+
+  // all[k][i] = value v[k] of lane i of this lane's group, for K scalars at once.  Two warp barriers: stores before
+  // loads, and loads before the next collective's stores.
+  static __device__ __forceinline__ float (*xch_warp())[kSlots * kSlot] {
+    __shared__ alignas(16) float xbuf[kXchMaxWarps][kXchMaxVals][kSlots * kSlot];
+    return xbuf[threadIdx.x >> 5];
+  }
+  template <int K>
+  static __device__ __forceinline__ void gather(const float (&v)[K], float (&all)[K][G]) {
+    static_assert(K <= kXchMaxVals, "exchange buffer too small");
+    const int ln = lane(), grp = ln / G, lg = ln - grp * G;
+    float (*mine)[kSlots * kSlot] = xch_warp();
+    NEOMPC_UNROLL
+    for (int k = 0; k < K; ++k) mine[k][grp * kSlot + lg] = v[k];
+    __syncwarp();
+    NEOMPC_UNROLL
+    for (int k = 0; k < K; ++k) {
+      const float4* src = reinterpret_cast<const float4*>(&mine[k][grp * kSlot]);
+      NEOMPC_UNROLL
+      for (int q = 0; q < kSlot / 4; ++q) {
+        if (4 * q + 4 <= G) {
+          const float4 t = src[q];
+          all[k][4 * q] = t.x; all[k][4 * q + 1] = t.y; all[k][4 * q + 2] = t.z; all[k][4 * q + 3] = t.w;
+        } else if (4 * q + 2 == G) {
+          const float2 t = *reinterpret_cast<const float2*>(&mine[k][grp * kSlot + 4 * q]);
+          all[k][4 * q] = t.x; all[k][4 * q + 1] = t.y;
+        } else {
+          NEOMPC_UNROLL
+          for (int e = 4 * q; e < G; ++e) all[k][e] = mine[k][grp * kSlot + e];
+        }
+      }
+    }
+    __syncwarp();
+  }
 #endif
   template <class Op>
   static NEOMPC_HD float reduce(float v, Op op) {
@@ -157,6 +209,13 @@ struct Grp {
     if (kPow2) {
       NEOMPC_UNROLL
       for (int o = G / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFullMask, v, o));
+    } else if (kXch) {
+      const float in[1] = {v};
+      float all[1][G];
+      gather<1>(in, all);
+      v = all[0][0];
+      NEOMPC_UNROLL
+      for (int i = 1; i < G; ++i) v = op(v, all[0][i]);
     } else {
       const int ln = lane(), lg = ln % G;
       NEOMPC_UNROLL
@@ -178,6 +237,36 @@ struct Grp {
   static NEOMPC_HD int imax(int v) {       // small non-negative flags/counters: exact in float
     return (int)reduce((float)v, Max());
   }
+  // two sums at once (one exchange for groups that use the shared-memory path)
+  static NEOMPC_HD void sum2(float& a, float& b) {
+#if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[2] = {a, b};
+      float all[2][G];
+      gather<2>(in, all);
+      a = all[0][0]; b = all[1][0];
+      NEOMPC_UNROLL
+      for (int i = 1; i < G; ++i) { a += all[0][i]; b += all[1][i]; }
+      return;
+    }
+#endif
+    a = sum(a); b = sum(b);
+  }
+  // two sums and a maximum at once
+  static NEOMPC_HD void sum2_max(float& a, float& b, float& c) {
+#if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[3] = {a, b, c};
+      float all[3][G];
+      gather<3>(in, all);
+      a = all[0][0]; b = all[1][0]; c = all[2][0];
+      NEOMPC_UNROLL
+      for (int i = 1; i < G; ++i) { a += all[0][i]; b += all[1][i]; c = fmaxf(c, all[2][i]); }
+      return;
+    }
+#endif
+    a = sum(a); b = sum(b); c = max(c);
+  }
   // the value lane 0 of the group holds
   static NEOMPC_HD float bcast0(float v, int lg) {
 #if defined(__CUDA_ARCH__)
@@ -189,6 +278,15 @@ struct Grp {
   // sum of v over the lanes of the group that come BEFORE this lane
   static NEOMPC_HD float excl_prefix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[1] = {v};
+      float all[1][G];
+      gather<1>(in, all);
+      float acc = 0 < lg ? all[0][0] : 0.0f;
+      NEOMPC_UNROLL
+      for (int i = 1; i + 1 < G; ++i) { if (i < lg) acc += all[0][i]; }
+      return acc;
+    }
     if (G > 1) {
       const int ln = lane();
       float incl = v;
@@ -204,9 +302,34 @@ struct Grp {
     (void)v; (void)lg;
     return 0.0f;
   }
+  // two exclusive prefix sums at once
+  static NEOMPC_HD void excl_prefix2(float a, float b, int lg, float* pa, float* pb) {
+#if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[2] = {a, b};
+      float all[2][G];
+      gather<2>(in, all);
+      float sa = 0 < lg ? all[0][0] : 0.0f, sb = 0 < lg ? all[1][0] : 0.0f;
+      NEOMPC_UNROLL
+      for (int i = 1; i + 1 < G; ++i) { if (i < lg) { sa += all[0][i]; sb += all[1][i]; } }
+      *pa = sa; *pb = sb;
+      return;
+    }
+#endif
+    *pa = excl_prefix(a, lg); *pb = excl_prefix(b, lg);
+  }
   // sum of v over the lanes of the group that come AFTER this lane
   static NEOMPC_HD float excl_suffix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[1] = {v};
+      float all[1][G];
+      gather<1>(in, all);
+      float acc = G - 1 > lg ? all[0][G - 1] : 0.0f;
+      NEOMPC_UNROLL
+      for (int i = G - 2; i > 0; --i) { if (i > lg) acc += all[0][i]; }
+      return acc;
+    }
     if (G > 1) {
       const int ln = lane();
       float incl = v;
@@ -221,6 +344,22 @@ struct Grp {
 #endif
     (void)v; (void)lg;
     return 0.0f;
+  }
+  // two exclusive suffix sums at once
+  static NEOMPC_HD void excl_suffix2(float a, float b, int lg, float* pa, float* pb) {
+#if defined(__CUDA_ARCH__)
+    if (kXch) {
+      const float in[2] = {a, b};
+      float all[2][G];
+      gather<2>(in, all);
+      float sa = G - 1 > lg ? all[0][G - 1] : 0.0f, sb = G - 1 > lg ? all[1][G - 1] : 0.0f;
+      NEOMPC_UNROLL
+      for (int i = G - 2; i > 0; --i) { if (i > lg) { sa += all[0][i]; sb += all[1][i]; } }
+      *pa = sa; *pb = sb;
+      return;
+    }
+#endif
+    *pa = excl_suffix(a, lg); *pb = excl_suffix(b, lg);
   }
   // true if the predicate holds for any lane of the WARP (all groups of a warp iterate in lock step)
   static NEOMPC_HD bool warp_any(bool p) {
@@ -567,8 +706,8 @@ struct Forward {
       ax += dx[j]; x[j] = ax;
       ay += dy[j]; y[j] = ay;
     }
-    const float xoff = Grp<G>::excl_prefix(ax, lg);
-    const float yoff = Grp<G>::excl_prefix(ay, lg);
+    float xoff, yoff;
+    Grp<G>::excl_prefix2(ax, ay, lg, &xoff, &yoff);
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) { x[j] += xoff; y[j] += yoff; }
   }
@@ -704,8 +843,8 @@ struct Forward {
       sx += x[j]; gx[j] = sx;                   // local inclusive suffix sums of the seeds left by cost()
       sy += y[j]; gy[j] = sy;
     }
-    const float sxoff = Grp<G>::excl_suffix(sx, lg);
-    const float syoff = Grp<G>::excl_suffix(sy, lg);
+    float sxoff, syoff;
+    Grp<G>::excl_suffix2(sx, sy, lg, &sxoff, &syoff);
     float sg = 0.0f;
     NEOMPC_UNROLL
     for (int j = S - 1; j >= 0; --j) {
@@ -1007,8 +1146,7 @@ struct Solver {
         pgn2 += pv * pv;
       }
     }
-    gd = Grp<G>::sum(gd);
-    pgn2 = Grp<G>::sum(pgn2);
+    Grp<G>::sum2(gd, pgn2);
     const bool qn_dir = (use_qn || use_pc) && (gd < -1e-4f * pgn2);
     // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
     // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
@@ -1100,7 +1238,7 @@ struct Solver {
         d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
       }
     }
-    sy = Grp<G>::sum(sy); yy = Grp<G>::sum(yy); smax = Grp<G>::max(smax);
+    Grp<G>::sum2_max(sy, yy, smax);
     if (active) {
       if (accepted) {
         if (!first && sy > P.pair_eps * yy && yy > 0.0f) {

@@ -1,5 +1,11 @@
+#!/bin/bash
+# scratch A/B: default build vs a variant library (NEOMPC_LIB), kernel-only lines
 O=gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/r2_gpu_tests_e.log
-python bench.py --steps 20 > $O/r2_bench_e.json 2> $O/r2_bench_e.err
-python bench.py --steps 10 --config c4 --no-cpu-baseline --sustained-s 0.3 > $O/r2_bench_e_c4.json 2>&1
-python bench.py --steps 20 --config c2 --no-cpu-baseline --sustained-s 0.3 > $O/r2_bench_e_c2.json 2>&1
+mkdir -p $O
+python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > $O/ab_gpu_tests.log
+for cfg in c3 c4 c5 c2; do
+  python bench.py --steps 20 --config $cfg --no-cpu-baseline --sustained-s 0.3 > $O/ab_new_$cfg.json 2> $O/ab_new_$cfg.err
+done
+for v in "$@"; do
+  NEOMPC_LIB=$PWD/neo_mpc_planner2_b200/libneompc_$v.so python bench.py --steps 20 --config c3 --no-cpu-baseline --sustained-s 0.3 > $O/ab_${v}_c3.json 2> $O/ab_${v}_c3.err
+done
