@@ -48,6 +48,12 @@ struct GroupMap {
   }
 };
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// keeps a value in a register: the compiler cannot re-derive it (here: the shared-window address of a static array,
+// which it would otherwise rebuild with S2UR + UMOV + ULEA at every use)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
 // cost tables staged once per block in shared memory
 struct SmemTables {
   float cost[kTableSize];
@@ -97,7 +103,6 @@ constexpr int min_blocks_for(int S) {
 // The 128/G request records of a block are contiguous in HBM (64 B each): one elected thread arms an mbarrier with the
 // byte count and issues ONE cp.async.bulk (SASS: UBLKCP) global -> shared; every lane then reads its group's record
 // from shared memory instead of issuing four 16-byte global loads per lane.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tma_stage_requests(neompc_request* s_req, unsigned long long* mbar,
                                                    const neompc_request* g_req, unsigned count) {
@@ -133,7 +138,7 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   extern __shared__ float hist_smem[];
   __shared__ SmemTables st;
   load_tables(st, lut_cost, lut_flag);
-  CostTables T{st.cost, st.flag};
+  CostTables T{st.cost, st.flag, opaque_u32(smem_addr(st.cost))};
   constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   __shared__ alignas(128) neompc_request s_req[kInstPerBlock];
   __shared__ alignas(8) unsigned long long s_mbar;
@@ -167,7 +172,7 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
             const float* __restrict__ u, float* __restrict__ J, float* __restrict__ grad) {
   __shared__ SmemTables st;
   load_tables(st, lut_cost, lut_flag);
-  CostTables T{st.cost, st.flag};
+  CostTables T{st.cost, st.flag, opaque_u32(smem_addr(st.cost))};
   constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const GroupMap<G> gm;
   const unsigned inst = blockIdx.x * kInstPerBlock + gm.slot;

@@ -110,6 +110,18 @@ struct SolverConst {
 struct CostTables {
   const float* cost;      // [kTableSize]  entry 256 = out-of-bounds (c = 1.0), entry 257 = no costmap (0)
   const uint8_t* flag;    // [kTableSize]
+  uint32_t cost_s;        // device: shared-space byte address of `cost` (the kernels stage the tables in shared memory)
+  // cost[byte_off / 4]: the hot lookups of Forward::cost address the shared window directly (ld.shared off a register
+  // base) — through the generic pointer the compiler rematerialises the window base (S2UR + UMOV + ULEA) at every site
+  NEOMPC_HD float cost_at_byte(uint32_t byte_off) const {
+#if defined(__CUDA_ARCH__)
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cost_s + byte_off));
+    return v;
+#else
+    return cost[byte_off >> 2];
+#endif
+  }
 };
 
 // Corner-packed costmap.  Entry (ix, iy), ix in [-pad, W + pad), iy in [-pad, H + pad), holds the bytes of the four
@@ -153,17 +165,23 @@ NEOMPC_HD int state_stride_for(int n_steps) { return 3 * n_steps + kStateExtra; 
 #ifndef NEOMPC_XCH
 #define NEOMPC_XCH 1
 #endif
+// power-of-two groups of at least this many lanes exchange through shared memory too (64: none — butterflies)
+#ifndef NEOMPC_XCH_POW2_MIN
+#define NEOMPC_XCH_POW2_MIN 64
+#endif
 #ifndef NEOMPC_BLOCK_THREADS
 #define NEOMPC_BLOCK_THREADS 64
 #endif
 constexpr int kXchMaxWarps = NEOMPC_BLOCK_THREADS / 32;   // warps per block (kernels.cuh launches exactly this block size)
-constexpr int kXchMaxVals = 3;         // scalars exchanged by one collective at most
+// first exchange array of the collectives that own their arrays (see Grp::gather)
+enum XchSite { kXsAny = 0, kXsZ = 4, kXsXY = 5, kXsJ = 7, kXsSuf2 = 9, kXsSufG = 11, kXsDot1 = 12, kXsDot2 = 13, kXsDesc = 14,
+               kXsPair = 15, kXchArrays = 19 };
 
 template <int G>
 struct Grp {
   static constexpr bool kPow2 = (G & (G - 1)) == 0;
   static constexpr int kPerWarp = 32 / G;          // groups (= instances) per warp
-  static constexpr bool kXch = NEOMPC_XCH && !kPow2;
+  static constexpr bool kXch = NEOMPC_XCH && G > 1 && (!kPow2 || G >= NEOMPC_XCH_POW2_MIN);
   static constexpr int kSlot = (G + 3) & ~3;       // floats per group slot of the exchange buffer (16-byte aligned)
   static constexpr int kSlots = (32 + G - 1) / G;  // incl. the partial group of leftover lanes
 #if defined(__CUDA_ARCH__)
@@ -171,15 +189,19 @@ struct Grp {
 
   // all[k][i] = value v[k] of lane i of this lane's group, for K scalars at once.  Two warp barriers: stores before
   // loads, and loads before the next collective's stores.
+  // The exchange buffer of a warp is kXchArrays arrays of one float per lane slot.  A collective names the first array
+  // it uses (`Site`) and takes K consecutive ones.  Site 0 (the default, arrays 0..3) ends with a second warp barrier so
+  // that it can be used anywhere; the hot collectives of Solver::pass own their arrays (XchSite) and skip that barrier:
+  // between two executions of the same site the warp always passes the barrier of another collective.
   static __device__ __forceinline__ float (*xch_warp())[kSlots * kSlot] {
-    __shared__ alignas(16) float xbuf[kXchMaxWarps][kXchMaxVals][kSlots * kSlot];
+    __shared__ alignas(16) float xbuf[kXchMaxWarps][kXchArrays][kSlots * kSlot];
     return xbuf[threadIdx.x >> 5];
   }
-  template <int K>
+  template <int K, int Site>
   static __device__ __forceinline__ void gather(const float (&v)[K], float (&all)[K][G]) {
-    static_assert(K <= kXchMaxVals, "exchange buffer too small");
+    static_assert(Site + K <= kXchArrays && (Site != 0 || K <= 4), "exchange buffer too small");
     const int ln = lane(), grp = ln / G, lg = ln - grp * G;
-    float (*mine)[kSlots * kSlot] = xch_warp();
+    float (*mine)[kSlots * kSlot] = xch_warp() + Site;
     NEOMPC_UNROLL
     for (int k = 0; k < K; ++k) mine[k][grp * kSlot + lg] = v[k];
     __syncwarp();
@@ -200,22 +222,31 @@ struct Grp {
         }
       }
     }
-    __syncwarp();
+    if (Site == 0) __syncwarp();
   }
 #endif
-  template <class Op>
+  template <int Site = 0, class Op>
   static NEOMPC_HD float reduce(float v, Op op) {
 #if defined(__CUDA_ARCH__)
-    if (kPow2) {
-      NEOMPC_UNROLL
-      for (int o = G / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFullMask, v, o));
-    } else if (kXch) {
+    if (kXch) {
       const float in[1] = {v};
       float all[1][G];
-      gather<1>(in, all);
-      v = all[0][0];
+      gather<1, Site>(in, all);
+      if (kPow2) {                        // pairwise tree (same order in every lane; short dependency chain)
+        NEOMPC_UNROLL
+        for (int w = G / 2; w > 0; w >>= 1) {
+          NEOMPC_UNROLL
+          for (int i = 0; i < w; ++i) all[0][i] = op(all[0][2 * i], all[0][2 * i + 1]);
+        }
+        v = all[0][0];
+      } else {
+        v = all[0][0];
+        NEOMPC_UNROLL
+        for (int i = 1; i < G; ++i) v = op(v, all[0][i]);
+      }
+    } else if (kPow2) {
       NEOMPC_UNROLL
-      for (int i = 1; i < G; ++i) v = op(v, all[0][i]);
+      for (int o = G / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFullMask, v, o));
     } else {
       const int ln = lane(), lg = ln % G;
       NEOMPC_UNROLL
@@ -232,18 +263,21 @@ struct Grp {
   }
   struct Add { NEOMPC_HD float operator()(float a, float b) const { return a + b; } };
   struct Max { NEOMPC_HD float operator()(float a, float b) const { return fmaxf(a, b); } };
-  static NEOMPC_HD float sum(float v) { return reduce(v, Add()); }
-  static NEOMPC_HD float max(float v) { return reduce(v, Max()); }
+  template <int Site = 0>
+  static NEOMPC_HD float sum(float v) { return reduce<Site>(v, Add()); }
+  template <int Site = 0>
+  static NEOMPC_HD float max(float v) { return reduce<Site>(v, Max()); }
   static NEOMPC_HD int imax(int v) {       // small non-negative flags/counters: exact in float
     return (int)reduce((float)v, Max());
   }
   // two sums at once (one exchange for groups that use the shared-memory path)
+  template <int Site = 0>
   static NEOMPC_HD void sum2(float& a, float& b) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
       const float in[2] = {a, b};
       float all[2][G];
-      gather<2>(in, all);
+      gather<2, Site>(in, all);
       a = all[0][0]; b = all[1][0];
       NEOMPC_UNROLL
       for (int i = 1; i < G; ++i) { a += all[0][i]; b += all[1][i]; }
@@ -252,20 +286,21 @@ struct Grp {
 #endif
     a = sum(a); b = sum(b);
   }
-  // two sums and a maximum at once
-  static NEOMPC_HD void sum2_max(float& a, float& b, float& c) {
+  // two sums and two maxima at once
+  template <int Site = 0>
+  static NEOMPC_HD void sum2_max2(float& a, float& b, float& c, float& d) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
-      const float in[3] = {a, b, c};
-      float all[3][G];
-      gather<3>(in, all);
-      a = all[0][0]; b = all[1][0]; c = all[2][0];
+      const float in[4] = {a, b, c, d};
+      float all[4][G];
+      gather<4, Site>(in, all);
+      a = all[0][0]; b = all[1][0]; c = all[2][0]; d = all[3][0];
       NEOMPC_UNROLL
-      for (int i = 1; i < G; ++i) { a += all[0][i]; b += all[1][i]; c = fmaxf(c, all[2][i]); }
+      for (int i = 1; i < G; ++i) { a += all[0][i]; b += all[1][i]; c = fmaxf(c, all[2][i]); d = fmaxf(d, all[3][i]); }
       return;
     }
 #endif
-    a = sum(a); b = sum(b); c = max(c);
+    a = sum(a); b = sum(b); c = max(c); d = max(d);
   }
   // the value lane 0 of the group holds
   static NEOMPC_HD float bcast0(float v, int lg) {
@@ -276,12 +311,13 @@ struct Grp {
     return v;
   }
   // sum of v over the lanes of the group that come BEFORE this lane
+  template <int Site = 0>
   static NEOMPC_HD float excl_prefix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
       const float in[1] = {v};
       float all[1][G];
-      gather<1>(in, all);
+      gather<1, Site>(in, all);
       float acc = 0 < lg ? all[0][0] : 0.0f;
       NEOMPC_UNROLL
       for (int i = 1; i + 1 < G; ++i) { if (i < lg) acc += all[0][i]; }
@@ -303,12 +339,13 @@ struct Grp {
     return 0.0f;
   }
   // two exclusive prefix sums at once
+  template <int Site = 0>
   static NEOMPC_HD void excl_prefix2(float a, float b, int lg, float* pa, float* pb) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
       const float in[2] = {a, b};
       float all[2][G];
-      gather<2>(in, all);
+      gather<2, Site>(in, all);
       float sa = 0 < lg ? all[0][0] : 0.0f, sb = 0 < lg ? all[1][0] : 0.0f;
       NEOMPC_UNROLL
       for (int i = 1; i + 1 < G; ++i) { if (i < lg) { sa += all[0][i]; sb += all[1][i]; } }
@@ -319,12 +356,13 @@ struct Grp {
     *pa = excl_prefix(a, lg); *pb = excl_prefix(b, lg);
   }
   // sum of v over the lanes of the group that come AFTER this lane
+  template <int Site = 0>
   static NEOMPC_HD float excl_suffix(float v, int lg) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
       const float in[1] = {v};
       float all[1][G];
-      gather<1>(in, all);
+      gather<1, Site>(in, all);
       float acc = G - 1 > lg ? all[0][G - 1] : 0.0f;
       NEOMPC_UNROLL
       for (int i = G - 2; i > 0; --i) { if (i > lg) acc += all[0][i]; }
@@ -346,12 +384,13 @@ struct Grp {
     return 0.0f;
   }
   // two exclusive suffix sums at once
+  template <int Site = 0>
   static NEOMPC_HD void excl_suffix2(float a, float b, int lg, float* pa, float* pb) {
 #if defined(__CUDA_ARCH__)
     if (kXch) {
       const float in[2] = {a, b};
       float all[2][G];
-      gather<2>(in, all);
+      gather<2, Site>(in, all);
       float sa = G - 1 > lg ? all[0][G - 1] : 0.0f, sb = G - 1 > lg ? all[1][G - 1] : 0.0f;
       NEOMPC_UNROLL
       for (int i = G - 2; i > 0; --i) { if (i > lg) { sa += all[0][i]; sb += all[1][i]; } }
@@ -695,7 +734,7 @@ struct Forward {
     float acc = 0.0f;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) { acc += u[j][2] * dt; z[j] = acc; }
-    const float zoff = Grp<G>::excl_prefix(acc, lg);
+    const float zoff = Grp<G>::template excl_prefix<kXsZ>(acc, lg);
     float ax = 0.0f, ay = 0.0f;
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
@@ -707,7 +746,7 @@ struct Forward {
       ay += dy[j]; y[j] = ay;
     }
     float xoff, yoff;
-    Grp<G>::excl_prefix2(ax, ay, lg, &xoff, &yoff);
+    Grp<G>::template excl_prefix2<kXsXY>(ax, ay, lg, &xoff, &yoff);
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) { x[j] += xoff; y[j] += yoff; }
   }
@@ -794,8 +833,8 @@ struct Forward {
         const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;                          // the cell containing the point
         float near;
         if (any_sur) {
-          const float k00 = T.cost[w & 0xffu], k10 = T.cost[(w >> 8) & 0xffu];      // w_costmap c^2 / N per corner
-          const float k01 = T.cost[(w >> 16) & 0xffu], k11 = T.cost[w >> 24];
+          const float k00 = T.cost_at_byte((w << 2) & 0x3fcu), k10 = T.cost_at_byte((w >> 6) & 0x3fcu);   // w_costmap c^2 / N per corner
+          const float k01 = T.cost_at_byte((w >> 14) & 0x3fcu), k11 = T.cost_at_byte((w >> 22) & 0x3fcu);
           near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
           const float ax = k10 - k00, bx = k11 - k01;
           const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
@@ -805,7 +844,7 @@ struct Forward {
           cmx[j] = ggx * cqs + ggy * sqs;                                           // gx = .. + cq x - sq y
           cmy[j] = ggy * cqs - ggx * sqs;                                           // gy = .. + sq x + cq y
         } else {
-          near = T.cost[(w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu];
+          near = T.cost_at_byte(((w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu) << 2);
           st += near;
         }
         st += near == P.k_lethal ? P.cm_wl : 0.0f;                                  // (the lethal entry is unique)
@@ -844,7 +883,7 @@ struct Forward {
       sy += y[j]; gy[j] = sy;
     }
     float sxoff, syoff;
-    Grp<G>::excl_suffix2(sx, sy, lg, &sxoff, &syoff);
+    Grp<G>::template excl_suffix2<kXsSuf2>(sx, sy, lg, &sxoff, &syoff);
     float sg = 0.0f;
     NEOMPC_UNROLL
     for (int j = S - 1; j >= 0; --j) {
@@ -853,7 +892,7 @@ struct Forward {
       sg += gz[j] - gx[j] * dy[j] + gy[j] * dx[j];
       gz[j] = sg;
     }
-    const float sgoff = Grp<G>::excl_suffix(sg, lg);
+    const float sgoff = Grp<G>::template excl_suffix<kXsSufG>(sg, lg);
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
@@ -1109,7 +1148,7 @@ struct Solver {
       float dot = 0.0f;
       NEOMPC_UNROLL
       for (int e = 0; e < 3 * S; ++e) dot += sp[(size_t)e * stride] * r[e / 3][e % 3];
-      dot = Grp<G>::sum(dot);
+      dot = Grp<G>::template sum<X ? kXsAny : kXsDot1>(dot);     // (m > 1: the site repeats back to back -> barrier-closed site 0)
       const float a = on ? sp[(size_t)(6 * S) * stride] * dot : 0.0f;
       sp[(size_t)(6 * S + 1) * stride] = a;
       NEOMPC_UNROLL
@@ -1128,7 +1167,7 @@ struct Solver {
       float dot = 0.0f;
       NEOMPC_UNROLL
       for (int e = 0; e < 3 * S; ++e) dot += yp[(size_t)e * stride] * r[e / 3][e % 3];
-      dot = Grp<G>::sum(dot);
+      dot = Grp<G>::template sum<X ? kXsAny : kXsDot2>(dot);
       const float b = on ? sp[(size_t)(6 * S + 1) * stride] - sp[(size_t)(6 * S) * stride] * dot : 0.0f;
       NEOMPC_UNROLL
       for (int e = 0; e < 3 * S; ++e) r[e / 3][e % 3] += b * sp[(size_t)e * stride];
@@ -1146,8 +1185,9 @@ struct Solver {
         pgn2 += pv * pv;
       }
     }
-    Grp<G>::sum2(gd, pgn2);
-    const bool qn_dir = (use_qn || use_pc) && (gd < -1e-4f * pgn2);
+    // descent test  pg.d < -1e-4 |pg|^2  as ONE group sum
+    const float desc = Grp<G>::template sum<kXsDesc>(gd + 1e-4f * pgn2);
+    const bool qn_dir = (use_qn || use_pc) && desc < 0.0f;
     // Binding constraints (at the boundary with the gradient pushing outward) stay fixed along the step
     // (two-metric projection): omega at a bound -> no omega step; (vx, vy) on the circle -> tangential step only.
     // Their projected gradient is zero, so pg . d — and with it the descent property — is unchanged.
@@ -1196,8 +1236,8 @@ struct Solver {
         gs += gsm[(size_t)(3 * j) * stride] * (xt[j][0] - u[j][0]) + gsm[(size_t)(3 * j + 1) * stride] * (xt[j][1] - u[j][1]) +
               gsm[(size_t)(3 * j + 2) * stride] * (xt[j][2] - u[j][2]);
       }
-      gs = Grp<G>::sum(gs);
-      const float ftrial = Grp<G>::sum(fw.template run<false>(P, T, I, xt, lg, sur));
+      float ftrial = fw.template run<false>(P, T, I, xt, lg, sur);
+      Grp<G>::template sum2<kXsJ>(gs, ftrial);
       NEOMPC_TRACE("   trial bt %d alpha %.4g gs %.4e df %.4e gd %.4e\n", bt, alpha, gs, ftrial - f, gd);
       if (!ls_done) {
         ++evals;
@@ -1224,7 +1264,7 @@ struct Solver {
     // ---- gradient and projected gradient at the last trial point (uniform work for the whole warp)
     float gn[S][3], pgn[S][3];
     fw.backward(P, I, xt, lg, gn);
-    const float pgmax_n = Grp<G>::max(projected_gradient<S, X>(P, xt, gn, pgn));
+    float pgmax_n = projected_gradient<S, X>(P, xt, gn, pgn);
     // secant pair of the projected-gradient map: s = x+ - x, y = pg(x+) - pg(x).  On an active disc
     // constraint y carries the curvature of the constraint, which a pair of plain gradients would miss.
     float sy = 0.0f, yy = 0.0f, smax = 0.0f;
@@ -1238,7 +1278,7 @@ struct Solver {
         d[j][q] = sv; r[j][q] = yv;            // reuse as (s, y)
       }
     }
-    Grp<G>::sum2_max(sy, yy, smax);
+    Grp<G>::template sum2_max2<kXsPair>(sy, yy, smax, pgmax_n);
     if (active) {
       if (accepted) {
         if (!first && sy > P.pair_eps * yy && yy > 0.0f) {
