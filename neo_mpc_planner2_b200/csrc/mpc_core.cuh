@@ -849,11 +849,17 @@ struct Forward {
         }
         st += near == P.k_lethal ? P.cm_wl : 0.0f;                                  // (the lethal entry is unique)
       }
-      const float ef = I.fyaw - z[j];
-      st += (i == P.N - 1) ? P.bt_term * (ef * ef) : 0.0f;                          // srv.py:267-268
       J += on ? st : 0.0f;
       x[j] = on ? -2.0f * P.a_trans * ex + cmx[j] : 0.0f;                           // adjoint seeds
       y[j] = on ? -2.0f * P.a_trans * ey + cmy[j] : 0.0f;
+    }
+    {                                                                               // terminal yaw term, srv.py:267-268
+      const int jl = P.N - 1 - lg * S;               // local index of the last step, if this lane holds it
+      float zl = z[0];
+      NEOMPC_UNROLL
+      for (int j = 1; j < S; ++j) zl = jl == j ? z[j] : zl;
+      const float ef = I.fyaw - zl;
+      J += (jl >= 0 && jl < S) ? P.bt_term * (ef * ef) : 0.0f;
     }
     return J;
   }
@@ -1132,7 +1138,6 @@ struct Solver {
 
     // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
     const bool use_qn = !first && !force_pg && hist_len > 0;
-    NEOMPC_UNROLL
     float* const pgs = pg_at(P, hist, stride);
     float* const gsm = g_at(P, hist, stride);
     NEOMPC_UNROLL

@@ -712,16 +712,40 @@ static int solve_batch_host(neompc_handle* h, const neompc_request* reqs, size_t
   // copies overlap (the copy engines for the two directions and the SMs are independent).  Problems are independent, so
   // chunking does not change any result.  What stays exposed is the H2D of the first chunk and the D2H of the last one.
   // Three chunks: measured on C3 with the board at its working clocks (profiles/host_chunks_r2.txt), 65536 requests in
-  // 0.664 / 0.624 / 0.611 / 0.641 / 0.653 / 0.771 ms with 1 / 2 / 3 / 4 / 6 / 8 chunks (kernel alone 0.55 ms).
+  // 0.664 / 0.624 / 0.611 / 0.641 / 0.653 / 0.771 ms with 1 / 2 / 3 / 4 / 6 / 8 chunks (kernel alone 0.55 ms); with the
+  // 0.443 ms kernel 0.548 / 0.537 / 0.497 / 0.530 ms with 1 / 2 / 3 / 4 equal chunks and 0.490 ms with sizes 1 : 4 : 6.
   const size_t n3 = 3 * (size_t)h->params.control_steps;
   static const int chunk_override = std::getenv("NEOMPC_CHUNKS") ? std::atoi(std::getenv("NEOMPC_CHUNKS")) : 0;   // tuning knob
   const int chunks = n >= 16384 ? (chunk_override > 0 ? chunk_override : 3) : 1;
-  const size_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+  // Chunk sizes: the first chunk is the small one — its H2D copy is the part of the transfer nothing can hide.  Relative
+  // weights, default 1 : 4 : 6 for three chunks (NEOMPC_CHUNK_WEIGHTS="a,b,c,..." for tuning; equal sizes otherwise).
+  static const std::vector<int> weight_override = [] {
+    std::vector<int> w;
+    if (const char* e = std::getenv("NEOMPC_CHUNK_WEIGHTS"))
+      for (const char* p = e; *p;) { w.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+    return w;
+  }();
+  size_t bound[17];
+  {
+    int w[16], wsum = 0;
+    for (int c = 0; c < chunks && c < 16; ++c) {
+      w[c] = (int)weight_override.size() == chunks ? std::max(1, weight_override[c])
+                                                   : (chunks == 3 && chunk_override == 0 ? (c == 0 ? 1 : c == 1 ? 4 : 6) : 1);
+      wsum += w[c];
+    }
+    size_t acc = 0;
+    bound[0] = 0;
+    for (int c = 0; c < chunks && c < 16; ++c) {
+      acc += (size_t)w[c];
+      bound[c + 1] = c + 1 == chunks ? n : std::min(n, (n * acc / (size_t)wsum + 63) / 64 * 64);
+    }
+  }
   cudaStream_t streams[2] = {h->stream, chunks > 1 ? h->stream2 : h->stream};
-  for (int c = 0; c < chunks; ++c) {
-    const size_t lo = (size_t)c * per;
+  for (int c = 0; c < chunks && c < 16; ++c) {
+    const size_t lo = bound[c];
     if (lo >= n) break;
-    const size_t cnt = n - lo < per ? n - lo : per;
+    const size_t cnt = bound[c + 1] - lo;
+    if (cnt == 0) continue;
     cudaStream_t s = streams[c & 1];
     NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs + lo, reqs + lo, cnt * sizeof(neompc_request), cudaMemcpyHostToDevice, s));
     rc = do_solve_device(h, h->d_reqs + lo, cnt, h->d_resp + lo, twist_out ? h->d_twist + lo * 3 : nullptr,

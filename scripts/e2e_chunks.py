@@ -36,6 +36,10 @@ if len(sys.argv) > 1:
     out["d2h_2MiB_ms"] = round((time.perf_counter() - t0) / 50 * 1e3, 4)
     print(json.dumps({"chunks": os.environ.get("NEOMPC_CHUNKS"), **out}))
 else:
-    for c in ("1", "2", "3", "4", "6", "8"):
-        r = subprocess.run([sys.executable, __file__, "x"], env=dict(os.environ, NEOMPC_CHUNKS=c), capture_output=True, text=True)
-        print(r.stdout.strip() or r.stderr[-300:])
+    for c, w in (("1", ""), ("2", ""), ("3", "1,1,1"), ("3", "1,3,4"), ("3", "1,2,4"), ("3", "2,3,3"), ("3", "1,4,6"), ("4", "1,2,4,4"),
+                 ("4", "1,3,6,6"), ("4", ""), ("2", "1,3")):
+        env = dict(os.environ, NEOMPC_CHUNKS=c)
+        if w:
+            env["NEOMPC_CHUNK_WEIGHTS"] = w
+        r = subprocess.run([sys.executable, __file__, "x"], env=env, capture_output=True, text=True)
+        print(w or "equal", r.stdout.strip() or r.stderr[-300:])
