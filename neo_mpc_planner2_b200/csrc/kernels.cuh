@@ -130,7 +130,7 @@ __device__ __forceinline__ void tma_stage_requests(neompc_request* s_req, unsign
   }
 }
 
-template <int G, int S, bool X>
+template <int G, int S, bool X, bool F>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_for(S))
 solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut_cost,
              const uint8_t* __restrict__ lut_flag, const neompc_request* __restrict__ reqs, unsigned n,
@@ -159,7 +159,7 @@ solve_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lu
   const unsigned inst = first + gm.slot;
   const bool valid = gm.lane_ok && inst < n;
   const neompc_request& rq = s_req[gm.slot];
-  solve_instance<G, S, X>(P, T, rq, valid, gm.lg, hist_smem + threadIdx.x, kBlockThreads,
+  solve_instance<G, S, X, F>(P, T, rq, valid, gm.lg, hist_smem + threadIdx.x, kBlockThreads,
                        valid ? out + inst : nullptr,
                        (valid && twist != nullptr) ? twist + 3 * (size_t)inst : nullptr,
                        (valid && plan != nullptr) ? plan + (size_t)inst * 3 * P.N : nullptr);
@@ -184,16 +184,24 @@ eval_kernel(const __grid_constant__ SolverConst P, const float* __restrict__ lut
                       (valid && grad != nullptr) ? grad + (size_t)inst * 3 * P.N : nullptr);
 }
 
-template <int G, int S, bool X>
-cudaError_t launch_solve_gs(const LaunchArgs& a) {
+template <int G, int S, bool X, bool F>
+cudaError_t launch_solve_gsf(const LaunchArgs& a) {
   const size_t smem = (size_t)kBlockThreads * hist_floats_per_lane<S>(a.P.m) * sizeof(float);
   constexpr int kInstPerBlock = GroupMap<G>::kPerBlock;
   const unsigned blocks_needed = (a.n + kInstPerBlock - 1) / kInstPerBlock;
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<G, S, X, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  solve_kernel<G, S, X><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
-                                                                       a.twist, a.plan);
+  solve_kernel<G, S, X, F><<<blocks_needed, kBlockThreads, smem, a.stream>>>(a.P, a.lut_cost, a.lut_flag, a.reqs, a.n, a.out,
+                                                                          a.twist, a.plan);
   return cudaGetLastError();
+}
+
+// The reference fast path has a second instantiation for horizons that fill the lane group exactly (G * S == control_steps:
+// C3's (5,2), C4's (10,2)): no padded steps, so the per-step masks of cost() and backward() fold away.  Same arithmetic.
+template <int G, int S, bool X>
+cudaError_t launch_solve_gs(const LaunchArgs& a) {
+  if (!X && G > 1 && a.P.N == G * S) return launch_solve_gsf<G, S, false, true>(a);
+  return launch_solve_gsf<G, S, X, false>(a);
 }
 
 template <int G, int S, bool X>

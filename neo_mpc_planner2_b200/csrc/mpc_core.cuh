@@ -200,27 +200,34 @@ struct Grp {
   template <int K, int Site>
   static __device__ __forceinline__ void gather(const float (&v)[K], float (&all)[K][G]) {
     static_assert(Site + K <= kXchArrays && (Site != 0 || K <= 4), "exchange buffer too small");
+    static_assert(K == 1 || K == 2 || K == 4, "one, two or four scalars per exchange");
     const int ln = lane(), grp = ln / G, lg = ln - grp * G;
-    float (*mine)[kSlots * kSlot] = xch_warp() + Site;
-    NEOMPC_UNROLL
-    for (int k = 0; k < K; ++k) mine[k][grp * kSlot + lg] = v[k];
+    // K scalars of a lane are stored side by side (one STS.32/.64/.128); a group's K*G floats start 16-byte aligned
+    constexpr int kSpan = (K * G + 3) & ~3;
+    static_assert(kSpan * kSlots <= K * kSlots * kSlot, "packed layout must fit the K arrays of the site");
+    float* base = &xch_warp()[Site][0] + grp * kSpan;
+    if (K == 1) base[lg] = v[0];
+    else if (K == 2) *reinterpret_cast<float2*>(base + 2 * lg) = make_float2(v[0], v[K > 1 ? 1 : 0]);
+    else *reinterpret_cast<float4*>(base + 4 * lg) = make_float4(v[0], v[K > 1 ? 1 : 0], v[K > 2 ? 2 : 0], v[K > 3 ? 3 : 0]);
     __syncwarp();
+    float flat[kSpan];
     NEOMPC_UNROLL
-    for (int k = 0; k < K; ++k) {
-      const float4* src = reinterpret_cast<const float4*>(&mine[k][grp * kSlot]);
-      NEOMPC_UNROLL
-      for (int q = 0; q < kSlot / 4; ++q) {
-        if (4 * q + 4 <= G) {
-          const float4 t = src[q];
-          all[k][4 * q] = t.x; all[k][4 * q + 1] = t.y; all[k][4 * q + 2] = t.z; all[k][4 * q + 3] = t.w;
-        } else if (4 * q + 2 == G) {
-          const float2 t = *reinterpret_cast<const float2*>(&mine[k][grp * kSlot + 4 * q]);
-          all[k][4 * q] = t.x; all[k][4 * q + 1] = t.y;
-        } else {
-          NEOMPC_UNROLL
-          for (int e = 4 * q; e < G; ++e) all[k][e] = mine[k][grp * kSlot + e];
-        }
+    for (int q = 0; q < kSpan / 4; ++q) {
+      if (4 * q + 4 <= K * G) {
+        const float4 t = *reinterpret_cast<const float4*>(base + 4 * q);
+        flat[4 * q] = t.x; flat[4 * q + 1] = t.y; flat[4 * q + 2] = t.z; flat[4 * q + 3] = t.w;
+      } else if (4 * q + 2 == K * G) {
+        const float2 t = *reinterpret_cast<const float2*>(base + 4 * q);
+        flat[4 * q] = t.x; flat[4 * q + 1] = t.y;
+      } else {
+        NEOMPC_UNROLL
+        for (int e = 4 * q; e < K * G; ++e) flat[e] = base[e];
       }
+    }
+    NEOMPC_UNROLL
+    for (int i = 0; i < G; ++i) {
+      NEOMPC_UNROLL
+      for (int k = 0; k < K; ++k) all[k][i] = flat[K * i + k];
     }
     if (Site == 0) __syncwarp();
   }
@@ -600,7 +607,7 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
 // box-and-disc projection and the accurate sincosf.  X = false is the reference fast path — no extension, disc inside the
 // box (P.disc_only), heading range within MUFU accuracy (P.fast_trig); the dispatcher picks it only when all three hold —
 // so that its hot loop carries none of the other code (merely being present cost 7-20 % there).
-template <int G, int S, bool X>
+template <int G, int S, bool X, bool F = false>   // F: G * S == control_steps, i.e. no padded step (the masks fold away)
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
 
@@ -821,7 +828,7 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
-      const bool on = i < P.N;
+      const bool on = F || i < P.N;
       const float ex = I.cx - x[j], ey = I.cy - y[j], eo = I.tyaw - z[j];
       float st = P.a_trans * (ex * ex + ey * ey) + P.b_orient * (eo * eo);          // srv.py:250-252
       const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
@@ -882,7 +889,7 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = S - 1; j >= 0; --j) {
       const int i = lg * S + j;
-      const bool on = i < P.N;
+      const bool on = F || i < P.N;
       gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
       gz[j] += (i == P.N - 1) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
       sx += x[j]; gx[j] = sx;                   // local inclusive suffix sums of the seeds left by cost()
@@ -902,7 +909,7 @@ struct Forward {
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
-      const bool on = i < P.N;
+      const bool on = F || i < P.N;
       const float rx = u[j][0] - I.v0x, ry = u[j][1] - I.v0y, rz = u[j][2] - I.v0z;
       const float kk = P.w_ctrl * rinv[j];
       g[j][0] = on ? dt * (c[j] * gx[j] + s[j] * gy[j]) + kk * rx : 0.0f;
@@ -1019,7 +1026,7 @@ NEOMPC_HD float projected_gradient(const SolverConst& P, const float (*u)[3], co
 // Every collective (shuffle / vote) in here is executed by all 32 lanes of the warp; per-group decisions are
 // predicates, never branches around a collective.
 // ---------------------------------------------------------------------------------------------------------
-template <int G, int S, bool X>
+template <int G, int S, bool X, bool F = false>
 struct Solver {
   static constexpr int PAIR = 6 * S + 2;
   // per-instance constants
@@ -1133,7 +1140,7 @@ struct Solver {
   // one iteration for every group of the warp (inactive groups compute and discard)
   NEOMPC_HD void pass(const SolverConst& P, const CostTables& T, float* hist, int stride, int lg) {
     const int m = X ? P.m : 1;                     // compile-time 1 on the fast path: the two loops below unroll away
-    Forward<G, S, X> fw;
+    Forward<G, S, X, F> fw;
     float d[S][3], xt[S][3], r[S][3];
 
     // ---- direction: two-loop recursion on the projected gradient (loops rolled: small code)
@@ -1449,10 +1456,10 @@ struct Solver {
 };
 
 // One optimizer() call for the instance owned by this lane group (one instance per group per launch).
-template <int G, int S, bool X>
+template <int G, int S, bool X, bool F = false>
 NEOMPC_HD void solve_instance(const SolverConst& P, const CostTables& T, const neompc_request& rq, bool valid,
                               int lg, float* hist, int stride, neompc_response* resp, float* twist, float* plan) {
-  Solver<G, S, X> sv;
+  Solver<G, S, X, F> sv;
   sv.prologue(P, T, rq, valid, lg, hist, stride);
   while (Grp<G>::warp_any(sv.active)) sv.pass(P, T, hist, stride, lg);
   sv.epilogue(P, T, rq, true, lg, resp, twist, plan);
