@@ -197,10 +197,11 @@ cudaError_t launch_solve_gsf(const LaunchArgs& a) {
 }
 
 // The reference fast path has a second instantiation for horizons that fill the lane group exactly (G * S == control_steps:
-// C3's (5,2), C4's (10,2)): no padded steps, so the per-step masks of cost() and backward() fold away.  Same arithmetic.
+// C3's (5,2), C4's (10,2)) on a handle with a costmap: no padded steps, so the per-step masks of cost() and backward() fold
+// away, and so do the costmap-present test and the bounds-checked sampling path.  Same arithmetic, bit-identical results.
 template <int G, int S, bool X>
 cudaError_t launch_solve_gs(const LaunchArgs& a) {
-  if (!X && G > 1 && a.P.N == G * S) return launch_solve_gsf<G, S, false, true>(a);
+  if (!X && G > 1 && a.P.N == G * S && a.P.cells4 != nullptr && a.P.pad_ok) return launch_solve_gsf<G, S, false, true>(a);
   return launch_solve_gsf<G, S, X, false>(a);
 }
 

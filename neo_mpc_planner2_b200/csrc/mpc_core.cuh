@@ -607,7 +607,9 @@ NEOMPC_HD Carry load_carry(const SolverConst& P, const neompc_request& rq, bool 
 // box-and-disc projection and the accurate sincosf.  X = false is the reference fast path — no extension, disc inside the
 // box (P.disc_only), heading range within MUFU accuracy (P.fast_trig); the dispatcher picks it only when all three hold —
 // so that its hot loop carries none of the other code (merely being present cost 7-20 % there).
-template <int G, int S, bool X, bool F = false>   // F: G * S == control_steps, i.e. no padded step (the masks fold away)
+// F ("full"): G * S == control_steps, i.e. no padded step, on a handle with a corner-packed costmap whose padding covers a
+// plan's reach — the per-step masks, the costmap-present test and the bounds-checked sampling path fold away (launch_solve_gs)
+template <int G, int S, bool X, bool F = false>
 struct Forward {
   float c[S], s[S], dx[S], dy[S], x[S], y[S], z[S], rinv[S];
 
@@ -772,7 +774,7 @@ struct Forward {
     const int ox = (int)flx, oy = (int)fly;
     bool inside = true;
     int idx = I.base4 + oy * P.pitch4 + ox;
-    if (Checked || !P.pad_ok) {                  // absolute entry; anything outside the padded array is outside the map
+    if (Checked || (!F && !P.pad_ok)) {          // absolute entry; anything outside the padded array is outside the map
       const float lim = 1.0e9f;
       const int ix = I.bx + (int)fminf(fmaxf(flx, -lim), lim), iy = I.by + (int)fminf(fmaxf(fly, -lim), lim);
       inside = ix >= -P.pad4 && ix < P.W + P.pad4 && iy >= -P.pad4 && iy < P.H + P.pad4;
@@ -799,7 +801,7 @@ struct Forward {
   NEOMPC_HD float cost(const SolverConst& P, const CostTables& T, const Instance& I, const float (*u)[3], int lg,
                        bool sur) {
     const bool bilinear = X && P.cm_mode == NEOMPC_COSTMAP_BILINEAR && P.cells != nullptr;   // uniform
-    const bool sampled = !bilinear && P.cells4 != nullptr;                                    // uniform
+    const bool sampled = F || (!bilinear && P.cells4 != nullptr);                             // uniform (F: the launcher checked)
     uint32_t word[S];
     float tx[S], ty[S];
     if (sampled) {
