@@ -863,12 +863,17 @@ struct Forward {
       y[j] = on ? -2.0f * P.a_trans * ey + cmy[j] : 0.0f;
     }
     {                                                                               // terminal yaw term, srv.py:267-268
-      const int jl = P.N - 1 - lg * S;               // local index of the last step, if this lane holds it
-      float zl = z[0];
-      NEOMPC_UNROLL
-      for (int j = 1; j < S; ++j) zl = jl == j ? z[j] : zl;
-      const float ef = I.fyaw - zl;
-      J += (jl >= 0 && jl < S) ? P.bt_term * (ef * ef) : 0.0f;
+      if (F) {                                       // full horizon: the last step is step S-1 of the last lane
+        const float ef = I.fyaw - z[S - 1];
+        J += lg == G - 1 ? P.bt_term * (ef * ef) : 0.0f;
+      } else {
+        const int jl = P.N - 1 - lg * S;             // local index of the last step, if this lane holds it
+        float zl = z[0];
+        NEOMPC_UNROLL
+        for (int j = 1; j < S; ++j) zl = jl == j ? z[j] : zl;
+        const float ef = I.fyaw - zl;
+        J += (jl >= 0 && jl < S) ? P.bt_term * (ef * ef) : 0.0f;
+      }
     }
     return J;
   }
@@ -893,7 +898,7 @@ struct Forward {
       const int i = lg * S + j;
       const bool on = F || i < P.N;
       gz[j] = on ? -2.0f * P.b_orient * (I.tyaw - z[j]) : 0.0f;
-      gz[j] += (i == P.N - 1) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
+      gz[j] += (F ? (j == S - 1 && lg == G - 1) : (i == P.N - 1)) ? -2.0f * P.bt_term * (I.fyaw - z[j]) : 0.0f;
       sx += x[j]; gx[j] = sx;                   // local inclusive suffix sums of the seeds left by cost()
       sy += y[j]; gy[j] = sy;
     }
@@ -1253,19 +1258,25 @@ struct Solver {
       float ftrial = fw.template run<false>(P, T, I, xt, lg, sur);
       Grp<G>::template sum2<kXsJ>(gs, ftrial);
       NEOMPC_TRACE("   trial bt %d alpha %.4g gs %.4e df %.4e gd %.4e\n", bt, alpha, gs, ftrial - f, gd);
-      if (!ls_done) {
-        ++evals;
-        ft = ftrial;
-        if (first || (ftrial <= f + 1e-4f * gs && gs < 0.0f)) { ls_done = true; accepted = true; }
+      // (bookkeeping as selects: groups of a warp differ here, and two small divergent branches per trial cost more than
+      //  the few instructions they would skip)
+      {
+        const bool run = !ls_done;
+        evals += run ? 1u : 0u;
+        ft = run ? ftrial : ft;
+        const bool ok = run && (first || (ftrial <= f + 1e-4f * gs && gs < 0.0f));
+        ls_done = ls_done || ok;
+        accepted = accepted || ok;
       }
       if (!Grp<G>::warp_any(!ls_done)) break;
-      if (!ls_done) {
-        // not a descent arc at all: give up on this direction at once (the fallback below takes over)
-        if (gs >= 0.0f && bt == 0 && qn_dir) { ls_done = true; }
+      {
+        const bool still = !ls_done;
         // safeguarded quadratic interpolation of the step length
         const float denom = 2.0f * (ftrial - f - gs);
         const float aq = denom > 0.0f ? div_approx(-gs, denom) : 0.5f;
-        alpha *= fminf(0.5f, fmaxf(0.1f, aq));
+        alpha = still ? alpha * fminf(0.5f, fmaxf(0.1f, aq)) : alpha;
+        // not a descent arc at all: give up on this direction at once (the fallback below takes over)
+        ls_done = ls_done || (still && gs >= 0.0f && bt == 0 && qn_dir);
       }
     }
     NEOMPC_TRACE("it %u f %.7f pgmax %.3e qn %d alpha %.4g acc %d ft %.7f evals %u hist %d\n", iters, f, pgmax,
