@@ -827,6 +827,39 @@ struct Forward {
         J += (hit && lg * S + j < P.N) ? P.w_fp_step : 0.0f;                        // srv.py:262-263 per step
       }
     }
+    // costmap term of each step and its lethal add-on (srv.py:246-247, 257-260), ONE warp-uniform branch for all steps
+    float cmv[S], lwv[S];
+    NEOMPC_UNROLL
+    for (int j = 0; j < S; ++j) { cmv[j] = 0.0f; lwv[j] = 0.0f; }
+    if (sampled) {
+      if (any_sur) {
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) {
+          const uint32_t w = word[j];
+          const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;                        // the cell containing the point
+          const float k00 = T.cost_at_byte((w << 2) & 0x3fcu), k10 = T.cost_at_byte((w >> 6) & 0x3fcu);   // w_costmap c^2 / N per corner
+          const float k01 = T.cost_at_byte((w >> 14) & 0x3fcu), k11 = T.cost_at_byte((w >> 22) & 0x3fcu);
+          const float near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
+          const float ax = k10 - k00, bx = k11 - k01;
+          const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
+          const float val = k0 + ty[j] * (k1 - k0);
+          const float ggx = ax + ty[j] * (bx - ax), ggy = k1 - k0;                 // per cell
+          cmv[j] = near + sf * (val - near);
+          cmx[j] = ggx * cqs + ggy * sqs;                                           // gx = .. + cq x - sq y
+          cmy[j] = ggy * cqs - ggx * sqs;                                           // gy = .. + sq x + cq y
+          lwv[j] = near == P.k_lethal ? P.cm_wl : 0.0f;                             // (the lethal entry is unique)
+        }
+      } else {
+        NEOMPC_UNROLL
+        for (int j = 0; j < S; ++j) {
+          const uint32_t w = word[j];
+          const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;
+          const float near = T.cost_at_byte(((w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu) << 2);
+          cmv[j] = near;
+          lwv[j] = near == P.k_lethal ? P.cm_wl : 0.0f;
+        }
+      }
+    }
     NEOMPC_UNROLL
     for (int j = 0; j < S; ++j) {
       const int i = lg * S + j;
@@ -837,26 +870,9 @@ struct Forward {
       const float r2 = fmaxf(rx * rx + ry * ry + rz * rz + P.eps2, 1e-24f);
       rinv[j] = rsqrt_f(r2);
       st += P.w_ctrl * (r2 * rinv[j]);                                              // srv.py:253-254 (smoothed)
-      if (sampled) {                                                                // srv.py:246-247, 257-260
-        const uint32_t w = word[j];
-        const bool hx = tx[j] >= 0.5f, hy = ty[j] >= 0.5f;                          // the cell containing the point
-        float near;
-        if (any_sur) {
-          const float k00 = T.cost_at_byte((w << 2) & 0x3fcu), k10 = T.cost_at_byte((w >> 6) & 0x3fcu);   // w_costmap c^2 / N per corner
-          const float k01 = T.cost_at_byte((w >> 14) & 0x3fcu), k11 = T.cost_at_byte((w >> 22) & 0x3fcu);
-          near = hy ? (hx ? k11 : k01) : (hx ? k10 : k00);
-          const float ax = k10 - k00, bx = k11 - k01;
-          const float k0 = k00 + tx[j] * ax, k1 = k01 + tx[j] * bx;
-          const float val = k0 + ty[j] * (k1 - k0);
-          const float ggx = ax + ty[j] * (bx - ax), ggy = k1 - k0;                   // per cell
-          st += near + sf * (val - near);
-          cmx[j] = ggx * cqs + ggy * sqs;                                           // gx = .. + cq x - sq y
-          cmy[j] = ggy * cqs - ggx * sqs;                                           // gy = .. + sq x + cq y
-        } else {
-          near = T.cost_at_byte(((w >> ((hx ? 8u : 0u) + (hy ? 16u : 0u))) & 0xffu) << 2);
-          st += near;
-        }
-        st += near == P.k_lethal ? P.cm_wl : 0.0f;                                  // (the lethal entry is unique)
+      if (sampled) {
+        st += cmv[j];
+        st += lwv[j];
       }
       J += on ? st : 0.0f;
       x[j] = on ? -2.0f * P.a_trans * ex + cmx[j] : 0.0f;                           // adjoint seeds
