@@ -30,6 +30,7 @@ struct LaunchArgs {
   float* grad;                 // device [n*3N] or null
   cudaStream_t stream;
   unsigned tiling_n;           // batch size the lane tiling is chosen for (0: n); the chunked host path passes the total
+  bool no_full;                // test knob NEOMPC_NO_FULL: never the full-horizon instantiation (launch_solve_gs)
 };
 
 // thread -> (instance slot of the block, lane inside the group): 32/G groups per warp, leftover lanes idle
@@ -198,10 +199,11 @@ cudaError_t launch_solve_gsf(const LaunchArgs& a) {
 
 // The reference fast path has a second instantiation for horizons that fill the lane group exactly (G * S == control_steps:
 // C3's (5,2), C4's (10,2)) on a handle with a costmap: no padded steps, so the per-step masks of cost() and backward() fold
-// away, and so do the costmap-present test and the bounds-checked sampling path.  Same arithmetic, bit-identical results.
+// away, and so do the costmap-present test and the bounds-checked sampling path.  Same source-level arithmetic; the compiler
+// contracts a few more multiply-adds without the selects, so the two agree to rounding (NEOMPC_NO_FULL forces F = false).
 template <int G, int S, bool X>
 cudaError_t launch_solve_gs(const LaunchArgs& a) {
-  if (!X && G > 1 && a.P.N == G * S && a.P.cells4 != nullptr && a.P.pad_ok) return launch_solve_gsf<G, S, false, true>(a);
+  if (!X && G > 1 && a.P.N == G * S && a.P.cells4 != nullptr && a.P.pad_ok && !a.no_full) return launch_solve_gsf<G, S, false, true>(a);
   return launch_solve_gsf<G, S, X, false>(a);
 }
 

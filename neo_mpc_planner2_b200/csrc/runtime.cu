@@ -32,6 +32,7 @@ struct neompc_handle {
   int G = 1, S = 1;         // lane-group tiling of batches (throughput)
   int Gl = 1, Sl = 1;       // tiling of tiny batches (latency): one step per lane where possible
   bool force_general = false;   // NEOMPC_FORCE_GENERAL=1: always the general kernel build (test knob)
+  bool no_full = false;         // NEOMPC_NO_FULL=1: never the full-horizon instantiation of the fast path (test knob)
   float* d_lut_cost = nullptr;
   uint8_t* d_lut_flag = nullptr;
   uint8_t* d_cells = nullptr;
@@ -424,6 +425,7 @@ int do_solve_device(neompc_handle* h, const neompc_request* d_reqs, size_t n, ne
   a.plan = d_plan;
   a.stream = s;
   a.tiling_n = (unsigned)tiling_n;
+  a.no_full = h->no_full;
   cudaError_t e = dispatch(h, false, a);
   if (e != cudaSuccess) return cuda_fail(h, e, "solve kernel launch");
   h->launches += 1;
@@ -467,6 +469,7 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   h->device = device;
   h->params = *params;
   h->force_general = std::getenv("NEOMPC_FORCE_GENERAL") != nullptr;
+  h->no_full = std::getenv("NEOMPC_NO_FULL") != nullptr;
 #define CREATE_CUDA(call)                                                                   \
   do {                                                                                      \
     cudaError_t e__ = (call);                                                               \

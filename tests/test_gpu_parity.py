@@ -417,6 +417,33 @@ def test_fast_path_kernel_agrees_with_general_kernel(Solver, monkeypatch):
     assert abs(float(oa["iters"].mean()) - float(ob["iters"].mean())) <= 0.2
 
 
+@pytest.mark.parametrize("cfg,n_steps,tiling", [("c3", 10, (5, 2)), ("c4", 20, (10, 2))])
+def test_full_horizon_instantiation_agrees(Solver, monkeypatch, cfg, n_steps, tiling):
+    """solve_kernel<G,S,false,true> — the instantiation for G*S == control_steps on a handle with a costmap: no padded-step
+    masks, no costmap-present test, no bounds-checked sampling path — against solve_kernel<G,S,false,false> (forced with
+    NEOMPC_NO_FULL).  Same algorithm and source-level arithmetic; the compiler contracts multiply-adds differently without
+    the selects, so the two agree to rounding: same costs reached, same iteration counts."""
+    wl, p, cm = setup_workload(cfg, 4096 * 5, n_steps)
+    res = {}
+    for no_full in (False, True):
+        if no_full:
+            monkeypatch.setenv("NEOMPC_NO_FULL", "1")
+        else:
+            monkeypatch.delenv("NEOMPC_NO_FULL", raising=False)
+        with Solver(wl.params) as s:
+            s.load_workload(wl)
+            assert tuple(s.tiling) == tiling
+            res[no_full] = s.solve(wl.requests, want_plan=True)
+    (oa, pa), (ob, pb) = res[False], res[True]
+    fpl = footprint_lethal_flags(wl, cm, wl.requests[:2048])
+    Ja = oracle.objective_batch(p, cm, wl.requests[:2048], pa[:2048].astype(np.float64), fp_lethal=fpl)
+    Jb = oracle.objective_batch(p, cm, wl.requests[:2048], pb[:2048].astype(np.float64), fp_lethal=fpl)
+    assert np.percentile(np.abs(Ja - Jb), 99) <= 2e-4, np.percentile(np.abs(Ja - Jb), [50, 99, 100])
+    assert np.median(np.abs(Ja - Jb)) <= 1e-6
+    assert abs(float(oa["iters"].mean()) - float(ob["iters"].mean())) <= 0.2
+    assert (oa["status"] != 1).mean() > 0.99 and (ob["status"] != 1).mean() > 0.99
+
+
 @pytest.mark.parametrize("n_total", [40001, 17000])
 def test_chunked_host_path_equals_device_path(Solver, n_total):
     """neompc_solve_batch pipelines large batches in chunks over two streams; results must equal the single-launch
