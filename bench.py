@@ -380,6 +380,11 @@ def run_ours(args):
     e2e_s = float(t.item())
     e2e_value = world * n * e2e_steps / e2e_s
     e2e_full = None
+    host_path = None
+    if world == 1:
+        host_path = {1: "pinned mailbox", 2: "staged copies pipelined with the solve in chunks (H2D requests, D2H results)",
+                     3: "zero-copy: the solve kernel reads the pinned request buffer and writes the pinned result buffer over PCIe "
+                        "itself (one launch); the bytes cross the bus inside the timed region all the same"}.get(solver.last_host_path)
     if world > 1:
         resp_host.copy_(d_out)
         torch.cuda.synchronize(dev)
@@ -505,7 +510,7 @@ def run_ours(args):
                          "note": "path is instruction/latency bound (FP32 + MUFU + shuffles), not HBM bound; see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * n * REQUEST_DTYPE.itemsize),
                     "d2h_bytes_per_step": int(n * 12) if world == 1 else int(world * world * n * 12),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "with_full_responses": e2e_full,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "with_full_responses": e2e_full, "host_path": host_path,
                     "api": "neompc_solve_batch_twists (pinned host buffers: requests in, (vx,vy,omega) out)" if world == 1 else
                            "per rank: H2D of its shard, neompc_solve_gather_device (solve + NCCL all-gather), D2H of all ranks' "
                            "(vx,vy,omega); bytes are whole-job totals"},

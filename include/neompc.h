@@ -338,10 +338,18 @@ int neompc_eval_objective(neompc_handle* h, const neompc_request* reqs, const fl
                           float* J, float* grad_or_null);
 /* Number of kernels this handle has launched so far. */
 uint64_t neompc_launch_count(const neompc_handle* h);
+/* How the last neompc_solve_batch / neompc_solve_batch_twists call moved its host buffers (measurement aid):
+ * MAILBOX  small batches through the handle's pinned mailbox;
+ * ZERO_COPY  the caller's buffers are page-locked and device-accessible (neompc_host_alloc, cudaHostAlloc,
+ *            cudaHostRegister): the solve kernel reads the requests and writes the results over PCIe itself, one launch;
+ * CHUNKED  pageable buffers: staged copies pipelined with the solve in chunks on two streams. */
+enum { NEOMPC_HOST_PATH_NONE = 0, NEOMPC_HOST_PATH_MAILBOX = 1, NEOMPC_HOST_PATH_CHUNKED = 2, NEOMPC_HOST_PATH_ZERO_COPY = 3 };
+int neompc_last_host_path(const neompc_handle* h);
 /* Lanes-per-instance / steps-per-lane the dispatcher uses for the current parameters. */
 int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* steps_per_lane);
 
-/* pinned host memory for the host-buffer entry points (optional; any host memory works) */
+/* pinned host memory for the host-buffer entry points (optional; any host memory works, pinned memory takes the
+ * zero-copy path of neompc_last_host_path) */
 int neompc_host_alloc(void** ptr, size_t bytes);
 int neompc_host_free(void* ptr);
 

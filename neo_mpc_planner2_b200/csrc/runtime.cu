@@ -33,6 +33,8 @@ struct neompc_handle {
   int Gl = 1, Sl = 1;       // tiling of tiny batches (latency): one step per lane where possible
   bool force_general = false;   // NEOMPC_FORCE_GENERAL=1: always the general kernel build (test knob)
   bool no_full = false;         // NEOMPC_NO_FULL=1: never the full-horizon instantiation of the fast path (test knob)
+  bool no_zero_copy = false;    // NEOMPC_NO_ZEROCOPY=1: host batches always go through staged copies (test / A-B knob)
+  int last_host_path = 0;       // neompc_last_host_path
   float* d_lut_cost = nullptr;
   uint8_t* d_lut_flag = nullptr;
   uint8_t* d_cells = nullptr;
@@ -470,6 +472,7 @@ int neompc_create(const neompc_params* params, int device, neompc_handle** out) 
   h->params = *params;
   h->force_general = std::getenv("NEOMPC_FORCE_GENERAL") != nullptr;
   h->no_full = std::getenv("NEOMPC_NO_FULL") != nullptr;
+  h->no_zero_copy = std::getenv("NEOMPC_NO_ZEROCOPY") != nullptr;
 #define CREATE_CUDA(call)                                                                   \
   do {                                                                                      \
     cudaError_t e__ = (call);                                                               \
@@ -697,6 +700,7 @@ static int solve_batch_host(neompc_handle* h, const neompc_request* reqs, size_t
     h->cap_twist = n * 3;
   }
   if (n <= kMailboxRequests) {                 // small batch: pinned mailbox in, mapped mailbox out (see solve_msgs)
+    h->last_host_path = NEOMPC_HOST_PATH_MAILBOX;
     const size_t n3s = n * 3 * (size_t)h->params.control_steps;
     std::memcpy(h->mb_reqs, reqs, n * sizeof(neompc_request));
     NEOMPC_CUDA(h, cudaMemcpyAsync(h->d_reqs, h->mb_reqs, n * sizeof(neompc_request), cudaMemcpyHostToDevice, h->stream));
@@ -711,6 +715,35 @@ static int solve_batch_host(neompc_handle* h, const neompc_request* reqs, size_t
     if (plan_or_null) std::memcpy(plan_or_null, h->mb_plan, n3s * sizeof(float));
     return check_state_errors(h);
   }
+  // Zero-copy: when the caller's buffers are page-locked and device-accessible (cudaHostAlloc / cudaHostRegister /
+  // neompc_host_alloc: with unified addressing every pinned allocation is), the kernel moves the data itself — the TMA
+  // bulk copy that stages a block's request tile reads the 64-byte records straight from host memory over PCIe, lane 0
+  // of a group writes its 12-byte twist (or 32-byte response) straight back — and ONE launch replaces the chunked copy
+  // pipeline below: no upload to wait for before the first block starts, no download after the last one finishes.  The
+  // transfers (4 MiB in, 768 KiB out at C3) ride under 0.39 ms of compute; what is left of the call is launch +
+  // synchronise.  Measured on C3: profiles/host_zero_copy_r2.txt.  Pageable buffers take the chunked path.
+  if (!h->no_zero_copy) {
+    auto mapped = [](const void* p) -> void* {
+      if (p == nullptr) return nullptr;
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    const neompc_request* zr = static_cast<const neompc_request*>(mapped(reqs));
+    neompc_response* zo = static_cast<neompc_response*>(mapped(out));
+    float* zt = static_cast<float*>(mapped(twist_out));
+    float* zp = static_cast<float*>(mapped(plan_or_null));
+    const bool all_mapped = zr != nullptr && (out == nullptr || zo != nullptr) && (twist_out == nullptr || zt != nullptr) &&
+                            (plan_or_null == nullptr || zp != nullptr) && (reinterpret_cast<uintptr_t>(zr) & 15u) == 0;
+    if (all_mapped) {
+      h->last_host_path = NEOMPC_HOST_PATH_ZERO_COPY;
+      rc = do_solve_device(h, zr, n, zo ? zo : h->d_resp, zt, zp, h->stream, n);
+      if (rc != NEOMPC_OK) return rc;
+      NEOMPC_CUDA(h, cudaStreamSynchronize(h->stream));
+      return check_state_errors(h);
+    }
+  }
+  h->last_host_path = NEOMPC_HOST_PATH_CHUNKED;
   // Large batches are cut into chunks on two streams, so the H2D copy of one chunk, the solve of another and the D2H
   // copies overlap (the copy engines for the two directions and the SMs are independent).  Problems are independent, so
   // chunking does not change any result.  What stays exposed is the H2D of the first chunk and the D2H of the last one.
@@ -1228,6 +1261,8 @@ int neompc_control_tick(neompc_handle* h, const neompc_carrot_params* cp, const 
 }
 
 uint64_t neompc_launch_count(const neompc_handle* h) { return h ? h->launches : 0; }
+
+int neompc_last_host_path(const neompc_handle* h) { return h ? h->last_host_path : NEOMPC_HOST_PATH_NONE; }
 
 int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* steps_per_lane) {
   if (!h) return NEOMPC_ERR_INVALID;

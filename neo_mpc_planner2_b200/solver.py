@@ -293,6 +293,11 @@ class BatchSolver:
         return int(self._lib.neompc_launch_count(self._h))
 
     @property
+    def last_host_path(self):
+        """neompc_last_host_path: 1 mailbox, 2 chunked staged copies, 3 zero-copy (pinned, device-accessible buffers)."""
+        return int(self._lib.neompc_last_host_path(self._h))
+
+    @property
     def tiling(self):
         g, s = ctypes.c_int(), ctypes.c_int()
         self._lib.neompc_get_tiling(self._h, ctypes.byref(g), ctypes.byref(s))

@@ -1,4 +1,3 @@
 #!/bin/bash
 O=gpurun_out
-mkdir -p $O
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "full_horizon" 2>&1 | tail -15 > $O/ab_fullhorizon_test.log
+timeout 400 python bench.py > $O/r2_bench_c3.json 2> $O/r2_bench_c3.err

@@ -36,10 +36,9 @@ if len(sys.argv) > 1:
     out["d2h_2MiB_ms"] = round((time.perf_counter() - t0) / 50 * 1e3, 4)
     print(json.dumps({"chunks": os.environ.get("NEOMPC_CHUNKS"), **out}))
 else:
-    for c, w in (("1", ""), ("2", ""), ("3", "1,1,1"), ("3", "1,3,4"), ("3", "1,2,4"), ("3", "2,3,3"), ("3", "1,4,6"), ("4", "1,2,4,4"),
-                 ("4", "1,3,6,6"), ("4", ""), ("2", "1,3")):
-        env = dict(os.environ, NEOMPC_CHUNKS=c)
-        if w:
-            env["NEOMPC_CHUNK_WEIGHTS"] = w
-        r = subprocess.run([sys.executable, __file__, "x"], env=env, capture_output=True, text=True)
-        print(w or "equal", r.stdout.strip() or r.stderr[-300:])
+    # first the zero-copy path (pinned buffers: the default), then the staged-copy pipeline with different chunkings
+    for label, extra in (("zero-copy (default for pinned buffers)", {}), ("staged copies, 3 chunks 1:4:6", {"NEOMPC_NO_ZEROCOPY": "1"}),
+                         ("staged copies, 3 equal chunks", {"NEOMPC_NO_ZEROCOPY": "1", "NEOMPC_CHUNKS": "3", "NEOMPC_CHUNK_WEIGHTS": "1,1,1"}),
+                         ("staged copies, 1 chunk", {"NEOMPC_NO_ZEROCOPY": "1", "NEOMPC_CHUNKS": "1"})):
+        r = subprocess.run([sys.executable, __file__, "x"], env=dict(os.environ, **extra), capture_output=True, text=True)
+        print(label, r.stdout.strip() or r.stderr[-300:])

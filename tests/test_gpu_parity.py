@@ -464,6 +464,37 @@ def test_chunked_host_path_equals_device_path(Solver, n_total):
     assert host.tobytes() == dev.tobytes()
 
 
+def test_zero_copy_host_path_equals_device_path(Solver):
+    """Page-locked, device-accessible host buffers take the zero-copy path of neompc_solve_batch[_twists]: the kernel reads
+    the requests and writes the results over PCIe itself, one launch.  Results equal the device path bit for bit; pageable
+    buffers (numpy) take the chunked path."""
+    import torch
+    from neo_mpc_planner2_b200.abi import RESPONSE_DTYPE
+    wl, p, cm = setup_workload("c3", 20001, 10)
+    n = wl.batch
+    with Solver(wl.params) as s:
+        s.load_workload(wl)
+        req = torch.from_numpy(wl.requests.view(np.uint8).reshape(n, 64).copy()).pin_memory()
+        out = torch.zeros((n, 32), dtype=torch.uint8).pin_memory()
+        tw = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+        plan = torch.zeros((n, 30), dtype=torch.float32).pin_memory()
+        s.solve_raw(req.data_ptr(), n, out.data_ptr(), plan.data_ptr())
+        assert s.last_host_path == 3
+        s.solve_twists_raw(req.data_ptr(), n, tw.data_ptr())
+        assert s.last_host_path == 3
+        pageable, plan_pageable = s.solve(wl.requests, want_plan=True)
+        assert s.last_host_path == 2
+        d_req = req.cuda()
+        d_out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+        s.solve_device(d_req.data_ptr(), n, d_out.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        dev = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESPONSE_DTYPE)
+    zc = np.frombuffer(out.numpy().tobytes(), dtype=RESPONSE_DTYPE)
+    assert zc.tobytes() == dev.tobytes() == pageable.tobytes()
+    assert plan.numpy().tobytes() == plan_pageable.tobytes()
+    assert np.array_equal(tw.numpy(), np.stack([dev["vx"], dev["vy"], dev["omega"]], axis=1))
+
+
 def test_msgs_entry_matches_request_entry(Solver):
     from neo_mpc_planner2_b200.server import requests_to_msgs
     wl, p, cm = setup_workload("c2", 256, 3)
