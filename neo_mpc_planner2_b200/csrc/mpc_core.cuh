@@ -187,11 +187,12 @@ struct Grp {
 #if defined(__CUDA_ARCH__)
   static __device__ __forceinline__ int lane() { return (int)(threadIdx.x & 31u); }
 
-  // all[k][i] = value v[k] of lane i of this lane's group, for K scalars at once.  Two warp barriers: stores before
-  // loads, and loads before the next collective's stores.
+  // gather(): all[k][i] = value v[k] of lane i of this lane's group, for K = 1, 2 or 4 scalars at once.
   // The exchange buffer of a warp is kXchArrays arrays of one float per lane slot.  A collective names the first array
-  // it uses (`Site`) and takes K consecutive ones.  Site 0 (the default, arrays 0..3) ends with a second warp barrier so
-  // that it can be used anywhere; the hot collectives of Solver::pass own their arrays (XchSite) and skip that barrier:
+  // it uses (`Site`) and owns K consecutive ones; inside them the K scalars of a lane lie side by side, so a lane stores
+  // with one STS.32/.64/.128 and reads its group's K*G floats with vector loads.  One warp barrier separates the stores
+  // from the loads.  Site 0 (the default, arrays 0..3) ends with a second barrier — loads before the next collective's
+  // stores — so that it can be used anywhere; the hot collectives of Solver::pass own their arrays (XchSite) and skip it:
   // between two executions of the same site the warp always passes the barrier of another collective.
   static __device__ __forceinline__ float (*xch_warp())[kSlots * kSlot] {
     __shared__ alignas(16) float xbuf[kXchMaxWarps][kXchArrays][kSlots * kSlot];
