@@ -253,7 +253,7 @@ def run_ours(args):
     else:
         solver = BatchSolver(wl.params, device=local, **knobs)
     solver.load_workload(wl)
-    G, S = solver.tiling
+    G, S = solver.tiling_for(n)          # what the dispatcher launches for this batch (C2's 4096 requests: the latency tiling)
 
     req_host = torch.from_numpy(wl.requests.view(np.uint8).reshape(n, REQUEST_DTYPE.itemsize)).pin_memory()
     resp_host = torch.empty((n, RESPONSE_DTYPE.itemsize), dtype=torch.uint8).pin_memory()

@@ -347,6 +347,9 @@ enum { NEOMPC_HOST_PATH_NONE = 0, NEOMPC_HOST_PATH_MAILBOX = 1, NEOMPC_HOST_PATH
 int neompc_last_host_path(const neompc_handle* h);
 /* Lanes-per-instance / steps-per-lane the dispatcher uses for the current parameters. */
 int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* steps_per_lane);
+/* ... and for a batch of n requests: batches small enough to be resident at once take the latency tiling (more lanes per
+ * instance, fewer steps per lane), larger ones the throughput tiling neompc_get_tiling reports. */
+int neompc_get_tiling_for(const neompc_handle* h, size_t n, int* lanes_per_instance, int* steps_per_lane);
 
 /* pinned host memory for the host-buffer entry points (optional; any host memory works, pinned memory takes the
  * zero-copy path of neompc_last_host_path) */

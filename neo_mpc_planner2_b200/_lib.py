@@ -17,7 +17,7 @@ EXPORTS = [
     "neompc_solve_batch", "neompc_solve_batch_device", "neompc_solve_msgs", "neompc_pack_requests",
     "neompc_set_plan", "neompc_build_requests", "neompc_build_requests_device",
     "neompc_local_plan", "neompc_local_plan_device",
-    "neompc_eval_objective", "neompc_launch_count", "neompc_last_host_path", "neompc_get_tiling", "neompc_host_alloc", "neompc_host_free",
+    "neompc_eval_objective", "neompc_launch_count", "neompc_last_host_path", "neompc_get_tiling", "neompc_get_tiling_for", "neompc_host_alloc", "neompc_host_free",
     "neompc_comm_unique_id", "neompc_comm_init", "neompc_comm_init_all", "neompc_comm_destroy", "neompc_comm_info",
     "neompc_shard_rows", "neompc_solve_gather_device", "neompc_gather_wait", "neompc_fleet_solve",
     "neompc_fleet_get_gathered", "neompc_control_tick", "neompc_solve_batch_twists",
@@ -91,6 +91,8 @@ def load():
     lib.neompc_eval_objective.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.neompc_launch_count.argtypes = [vp]
     lib.neompc_launch_count.restype = ctypes.c_uint64
+    lib.neompc_get_tiling_for.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    lib.neompc_get_tiling_for.restype = ctypes.c_int
     lib.neompc_last_host_path.argtypes = [vp]
     lib.neompc_last_host_path.restype = ctypes.c_int
     lib.neompc_get_tiling.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]

@@ -1271,6 +1271,14 @@ int neompc_get_tiling(const neompc_handle* h, int* lanes_per_instance, int* step
   return NEOMPC_OK;
 }
 
+int neompc_get_tiling_for(const neompc_handle* h, size_t n, int* lanes_per_instance, int* steps_per_lane) {
+  if (!h) return NEOMPC_ERR_INVALID;
+  const bool latency = n * (size_t)h->Gl <= (size_t)h->sm_count * 16u * 32u;      // the rule of dispatch()
+  if (lanes_per_instance) *lanes_per_instance = latency ? h->Gl : h->G;
+  if (steps_per_lane) *steps_per_lane = latency ? h->Sl : h->S;
+  return NEOMPC_OK;
+}
+
 int neompc_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return NEOMPC_ERR_INVALID;
   return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? NEOMPC_OK : NEOMPC_ERR_CUDA;

@@ -292,6 +292,13 @@ class BatchSolver:
     def launch_count(self):
         return int(self._lib.neompc_launch_count(self._h))
 
+    def tiling_for(self, n):
+        """(lanes per instance, steps per lane) the dispatcher uses for a batch of n requests (latency tiling while the batch
+        is resident at once, else the throughput tiling of `tiling`)."""
+        g, s = ctypes.c_int(), ctypes.c_int()
+        self._lib.neompc_get_tiling_for(self._h, int(n), ctypes.byref(g), ctypes.byref(s))
+        return g.value, s.value
+
     @property
     def last_host_path(self):
         """neompc_last_host_path: 1 mailbox, 2 chunked staged copies, 3 zero-copy (pinned, device-accessible buffers)."""
