@@ -1,4 +1,5 @@
 #!/bin/bash
 O=gpurun_out
-timeout 70 python bench.py --config c2 --steps 20 --no-cpu-baseline --sustained-s 0.2 > $O/ab_c2_label.json 2> $O/ab_c2_label.err
-timeout 60 python bench.py --steps 5 --no-cpu-baseline --sustained-s 0.2 > $O/ab_c3_label.json 2> $O/ab_c3_label.err
+for cfg in c4 c5 c2; do
+timeout 60 python bench.py --config $cfg --steps 10 --no-cpu-baseline --sustained-s 0.2 > $O/ab_zc_$cfg.json 2> $O/ab_zc_$cfg.err
+done
